@@ -1,0 +1,149 @@
+/*
+ * modfx.h -- C ABI of libmodfx.so: B200 (sm_100a) renderer for the effect hot path of
+ * christhetree/mod_extraction.
+ *
+ * The reference has no FFI layer; its boundary for this path is a set of Python
+ * signatures.  Each entry point below names the reference
+ * interface it replaces (file:line relative to the reference root).  All pointers
+ * named *_dev / x / y / mod are DEVICE pointers unless the function name ends in
+ * _host; everything is float32, contiguous, row-major.  `stream` is a cudaStream_t
+ * passed as void* (0 = legacy default stream).  Calls are asynchronous on `stream`
+ * (the _host variants synchronise before returning).  No hidden state is kept
+ * between calls; calls on different streams may run concurrently.
+ *
+ * Every function returns MODFX_OK (0) or a negative modfx_status; on failure
+ * modfx_last_error() returns a thread-local message.  There is no CPU fallback:
+ * without a CUDA device every compute entry point returns MODFX_ERR_CUDA.
+ */
+#ifndef MODFX_H_
+#define MODFX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MODFX_ABI_VERSION 1
+
+typedef enum {
+    MODFX_OK = 0,
+    MODFX_ERR_INVALID = -1,      /* bad shape / null pointer / out-of-range scalar */
+    MODFX_ERR_UNSUPPORTED = -2,  /* valid request the kernels do not cover (e.g. delay line > smem) */
+    MODFX_ERR_CUDA = -3          /* CUDA runtime error (message holds cudaGetErrorString) */
+} modfx_status;
+
+/* LFO shapes of make_mod_signal, mod_extraction/modulations.py:25 */
+typedef enum {
+    MODFX_SHAPE_COS = 0,
+    MODFX_SHAPE_RECT_COS = 1,
+    MODFX_SHAPE_INV_RECT_COS = 2,
+    MODFX_SHAPE_TRI = 3,
+    MODFX_SHAPE_SAW = 4,
+    MODFX_SHAPE_RSAW = 5,
+    MODFX_SHAPE_SQR = 6
+} modfx_shape;
+
+/*
+ * A per-example effect parameter: the reference accepts `Union[float, Tensor(B,)]`
+ * (fx.py:75-79).  dev != NULL  -> (B,) float32 device array (torch-tensor semantics:
+ * float32 arithmetic); dev == NULL -> python-float semantics: `value` is combined with
+ * other python numbers in double and rounded to float32 where it meets a tensor.
+ */
+typedef struct {
+    const float* dev;
+    double value;
+} modfx_param;
+
+/* Where the modulation signal comes from. */
+typedef enum {
+    MODFX_MOD_AUDIO_RATE = 0,   /* mod (B,N) or (B,C,N) float32: the literal forward(x, mod_sig) */
+    MODFX_MOD_CONTROL_RATE = 1, /* mod (B,n_lo): upsampled in-kernel exactly like
+                                   util.linear_interpolate_last_dim(mod, N) (util.py:15-29,
+                                   called at data_modules.py:454-455) */
+    MODFX_MOD_LFO = 2           /* synthesised in-kernel from per-example LFO parameters like
+                                   make_mod_signal(n_lo, sr_lo, freq, phase, shape, exp)
+                                   (modulations.py:16-57; datasets.py:382), then upsampled
+                                   to N as above when n_lo != N */
+} modfx_mod_kind;
+
+typedef struct {
+    int32_t kind;            /* modfx_mod_kind */
+    const float* mod;        /* AUDIO_RATE / CONTROL_RATE */
+    int32_t mod_has_ch;      /* AUDIO_RATE: 1 if mod is (B,C,N), 0 if (B,N) */
+    int64_t n_lo;            /* CONTROL_RATE / LFO: points per example */
+    float sr_lo;             /* LFO: sample rate the LFO is generated at */
+    const float* lfo_freq;   /* LFO: (B,) Hz  (already halved for rect shapes, modulations.py:26-29) */
+    const float* lfo_phase;  /* LFO: (B,) rad (already halved for rect shapes) */
+    const int32_t* lfo_shape;/* LFO: (B,) modfx_shape */
+    const float* lfo_exp;    /* LFO: (B,) exponent, or NULL for 1.0 */
+} modfx_mod_source;
+
+int modfx_abi_version(void);
+const char* modfx_last_error(void);
+/* Number of CUDA devices visible to the library (0 if none / no driver). */
+int modfx_device_count(void);
+
+/*
+ * Replaces MonoFlangerChorusModule.forward / apply_effect, mod_extraction/fx.py:72-130
+ * (ctor arithmetic fx.py:40-42 gives Mmin, Mlfo).  Bit-exact with the reference for
+ * identical x / mod / parameters (IEEE round-to-nearest, no FMA contraction).
+ *   x, y          (B, C, N)
+ *   example_index optional (n_items,) int32: render only these examples (rows of x / y /
+ *                 mod / parameter arrays are still indexed by the example id); NULL = all B.
+ */
+int modfx_flanger_chorus_f32(const float* x, float* y, int32_t B, int32_t C, int64_t N,
+                             int32_t max_min_delay_samples, int32_t max_lfo_delay_samples,
+                             const modfx_mod_source* mod,
+                             modfx_param feedback, modfx_param min_delay_width, modfx_param width,
+                             modfx_param depth, modfx_param mix,
+                             const int32_t* example_index, int32_t n_items, void* stream);
+
+/* Replaces apply_tremolo, mod_extraction/fx.py:13-22. */
+int modfx_tremolo_f32(const float* x, float* y, int32_t B, int32_t C, int64_t N,
+                      const modfx_mod_source* mod, modfx_param mix, void* stream);
+
+/*
+ * Replaces make_mod_signal / make_rand_mod_signal's inner call, modulations.py:16-57,98:
+ * out (B, n) = LFO per example.  freq/phase already halved for rect shapes.
+ */
+int modfx_lfo_f32(float* out, int32_t B, int64_t n, float sr, const float* freq, const float* phase,
+                  const int32_t* shape, const float* exp_or_null, void* stream);
+
+/* Replaces util.linear_interpolate_last_dim, mod_extraction/util.py:15-29 (F.interpolate
+ * mode="linear").  in (rows, I) -> out (rows, O). */
+int modfx_interp_linear_f32(const float* in, float* out, int64_t rows, int64_t I, int64_t O,
+                            int32_t align_corners, void* stream);
+
+/*
+ * Replaces Spectral2DCNN.spectrogram + clip + log, mod_extraction/models.py:170-175,199,207-208
+ * (torchaudio MelSpectrogram n_fft=1024, hop 256, center/reflect, periodic Hann, power 2).
+ *   x         (R, T) rows = batch*channels
+ *   out       (R, n_mels, T/hop + 1)
+ *   window    (n_fft,) device
+ *   fb_start, fb_count (n_mels,) int32 device: first FFT bin and number of taps of each mel band
+ *   fb_weight (n_mels, fb_stride) float32 device: tap weights, zero padded
+ * Supported: n_fft == 1024, hop == 256.
+ */
+int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T, int32_t n_fft, int32_t hop,
+                     int32_t n_mels, const float* window, const int32_t* fb_start,
+                     const int32_t* fb_count, const float* fb_weight, int32_t fb_stride, float eps,
+                     void* stream);
+
+/*
+ * Replaces PedalboardPhaserDataset.apply_pedalboard_phaser's DSP, mod_extraction/datasets.py:455-482
+ * (pedalboard.Phaser -> juce::dsp::Phaser, 6 TPT all-pass stages + feedback, cutoff updated every
+ * 4th sample).  PARITY UNPINNED: checked only against this repo's own CPU restatement.
+ *   x, y (B, N); per-example (B,) device arrays; `block` = host block size of pedalboard (8192).
+ *   workspace: device scratch of modfx_phaser_workspace_bytes(B, N) bytes.
+ */
+int64_t modfx_phaser_workspace_bytes(int32_t B, int64_t N);
+int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, const float* rate_hz,
+                     const float* depth, const float* centre_hz, const float* feedback,
+                     const float* mix, int32_t block, const int32_t* example_index, int32_t n_items,
+                     void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODFX_H_ */

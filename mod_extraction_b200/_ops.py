@@ -1,0 +1,178 @@
+"""Thin tensor-level wrappers over the libmodfx C ABI (one function per entry point).
+
+These take CUDA float32 tensors, launch on the current torch stream and return new tensors;
+they are what ``torch.ops.modfx.*`` dispatches to (CUDA key only -- see ``_torch_ops.py``) and what
+the reference-signature shims in ``fx.py`` / ``modulations.py`` / ``util.py`` / ``models.py`` call.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Union
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import ModfxModSource, ModfxParam
+
+Param = Union[float, Tensor]
+
+
+def _require_cuda(t: Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"modfx: `{name}` must be a CUDA tensor (got {t.device}); there is no CPU kernel")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"modfx: `{name}` must be float32 (got {t.dtype})")
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class _Keep:
+    """Holds temporaries alive until the call has been enqueued."""
+
+    def __init__(self):
+        self.items = []
+
+    def __call__(self, t):
+        self.items.append(t)
+        return t
+
+
+def as_param(p: Param, B: int, device, keep: _Keep, name: str) -> ModfxParam:
+    """float -> python-scalar semantics; (B,) tensor -> float32 device array (fx.py:46-70)."""
+    if isinstance(p, Tensor):
+        if p.shape != (B,):
+            raise AssertionError(f"{name}: expected shape ({B},), got {tuple(p.shape)}")
+        t = keep(p.detach().to(device=device, dtype=torch.float32, non_blocking=True).contiguous())
+        return ModfxParam(t.data_ptr(), 0.0)
+    return ModfxParam(None, float(p))
+
+
+class ModSource:
+    """Python-side description of where the modulation signal comes from (modfx_mod_source)."""
+
+    def __init__(self, kind: int, mod: Optional[Tensor] = None, n_lo: int = 0, sr_lo: float = 0.0,
+                 freq: Optional[Tensor] = None, phase: Optional[Tensor] = None, shape: Optional[Tensor] = None,
+                 exp: Optional[Tensor] = None):
+        self.kind, self.mod, self.n_lo, self.sr_lo = kind, mod, n_lo, sr_lo
+        self.freq, self.phase, self.shape, self.exp = freq, phase, shape, exp
+
+    @staticmethod
+    def audio_rate(mod_sig: Tensor) -> "ModSource":
+        return ModSource(_lib.MOD_AUDIO_RATE, mod=mod_sig)
+
+    @staticmethod
+    def control_rate(mod_lo: Tensor) -> "ModSource":
+        return ModSource(_lib.MOD_CONTROL_RATE, mod=mod_lo, n_lo=mod_lo.size(-1))
+
+    @staticmethod
+    def lfo(n_lo: int, sr_lo: float, freq: Tensor, phase: Tensor, shape: Tensor, exp: Optional[Tensor] = None):
+        return ModSource(_lib.MOD_LFO, n_lo=n_lo, sr_lo=sr_lo, freq=freq, phase=phase, shape=shape, exp=exp)
+
+    def to_c(self, B: int, C: int, N: int, device, keep: _Keep) -> ModfxModSource:
+        s = ModfxModSource()
+        s.kind = self.kind
+        if self.kind in (_lib.MOD_AUDIO_RATE, _lib.MOD_CONTROL_RATE):
+            m = self.mod
+            _require_cuda(m, "mod_sig")
+            m = keep(m.contiguous())
+            has_ch = 0
+            if self.kind == _lib.MOD_AUDIO_RATE:
+                if m.ndim == 3:
+                    if m.size(1) == C and C > 1:
+                        has_ch = 1
+                    elif m.size(1) == 1 or C == 1:
+                        m = keep(m.reshape(m.size(0), m.size(-1)))      # (B,1,N): broadcast over channels
+                    else:
+                        raise AssertionError("mod_sig channel dim must be 1 or n_ch")
+                assert m.size(0) == B and m.size(-1) == N
+            else:
+                assert m.ndim == 2 and m.size(0) == B
+            s.mod = m.data_ptr()
+            s.mod_has_ch = has_ch
+            s.n_lo = m.size(-1)
+        else:
+            f = keep(self.freq.to(device=device, dtype=torch.float32).contiguous())
+            p = keep(self.phase.to(device=device, dtype=torch.float32).contiguous())
+            sh = keep(self.shape.to(device=device, dtype=torch.int32).contiguous())
+            assert f.shape == (B,) and p.shape == (B,) and sh.shape == (B,)
+            s.lfo_freq, s.lfo_phase, s.lfo_shape = f.data_ptr(), p.data_ptr(), sh.data_ptr()
+            if self.exp is not None:
+                e = keep(self.exp.to(device=device, dtype=torch.float32).contiguous())
+                assert e.shape == (B,)
+                s.lfo_exp = e.data_ptr()
+            s.n_lo = int(self.n_lo)
+            s.sr_lo = float(self.sr_lo)
+        return s
+
+
+def flanger_chorus(x: Tensor, mod: ModSource, m_min: int, m_lfo: int, feedback: Param, min_delay_width: Param,
+                   width: Param, depth: Param, mix: Param, example_index: Optional[Tensor] = None,
+                   out: Optional[Tensor] = None) -> Tensor:
+    _require_cuda(x, "x")
+    assert x.ndim == 3
+    x = x.contiguous()
+    B, C, N = x.shape
+    y = torch.empty_like(x) if out is None else out
+    assert y.is_cuda and y.is_contiguous() and y.shape == x.shape and y.dtype == torch.float32
+    keep = _Keep()
+    with torch.cuda.device(x.device):
+        src = mod.to_c(B, C, N, x.device, keep)
+        args = [as_param(p, B, x.device, keep, n) for p, n in
+                ((feedback, "feedback"), (min_delay_width, "min_delay_width"), (width, "width"),
+                 (depth, "depth"), (mix, "mix"))]
+        idx_ptr, n_items = ctypes.c_void_p(0), 0
+        if example_index is not None:
+            idx = keep(example_index.to(device=x.device, dtype=torch.int32).contiguous())
+            idx_ptr, n_items = ctypes.c_void_p(idx.data_ptr()), idx.numel()
+            if n_items == 0:
+                return y
+        _lib.check(_lib.lib().modfx_flanger_chorus_f32(_ptr(x), _ptr(y), B, C, N, m_min, m_lfo, ctypes.byref(src),
+                                                       *args, idx_ptr, n_items, _stream()))
+    return y
+
+
+def tremolo(x: Tensor, mod: ModSource, mix: Param) -> Tensor:
+    _require_cuda(x, "x")
+    assert x.ndim == 3
+    x = x.contiguous()
+    B, C, N = x.shape
+    y = torch.empty_like(x)
+    keep = _Keep()
+    with torch.cuda.device(x.device):
+        src = mod.to_c(B, C, N, x.device, keep)
+        _lib.check(_lib.lib().modfx_tremolo_f32(_ptr(x), _ptr(y), B, C, N, ctypes.byref(src),
+                                                as_param(mix, B, x.device, keep, "mix"), _stream()))
+    return y
+
+
+def lfo(n: int, sr: float, freq: Tensor, phase: Tensor, shape: Tensor, exp: Optional[Tensor] = None) -> Tensor:
+    _require_cuda(freq, "freq")
+    B = freq.numel()
+    out = torch.empty((B, n), device=freq.device, dtype=torch.float32)
+    keep = _Keep()
+    with torch.cuda.device(freq.device):
+        f = keep(freq.contiguous())
+        p = keep(phase.to(device=freq.device, dtype=torch.float32).contiguous())
+        s = keep(shape.to(device=freq.device, dtype=torch.int32).contiguous())
+        e = None if exp is None else keep(exp.to(device=freq.device, dtype=torch.float32).contiguous())
+        _lib.check(_lib.lib().modfx_lfo_f32(_ptr(out), B, n, float(sr), _ptr(f), _ptr(p), _ptr(s), _ptr(e), _stream()))
+    return out
+
+
+def interp_linear(x: Tensor, n: int, align_corners: bool = True) -> Tensor:
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    I = x.size(-1)
+    rows = x.numel() // I
+    out = torch.empty(x.shape[:-1] + (n,), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().modfx_interp_linear_f32(_ptr(x), _ptr(out), rows, I, n, 1 if align_corners else 0,
+                                                      _stream()))
+    return out

@@ -1,0 +1,442 @@
+// Flanger / chorus modulated fractional-delay line with feedback (and tremolo).
+//
+// Replaces MonoFlangerChorusModule.apply_effect (reference mod_extraction/fx.py:72-119), whose
+// python loop costs ~105 us per time step.  Bit-exact with it: every float32 operation of the
+// reference is one IEEE-RN operation here (explicit __f*_rn intrinsics, never contracted).
+//
+// Parallelisation (DESIGN.md "E1"): the recurrence v[n] = x[n] + fb*interp(v[n-kp], v[n-kq]) is
+// sequential in time per delay line, but a sample only depends on samples at least
+// `near = min(kp,kq)` steps back.  One warp owns one delay line (example x channel); the written
+// values v live in a shared-memory ring indexed by time.  A tile of 128 samples (4 per lane) is
+// rendered in one shot when every dependency falls before the tile (always true for chorus,
+// true for flanger while the delay exceeds 128 samples); otherwise 32-sample blocks are resolved
+// as "waves" of independent prefixes, and stretches with a 1-2 sample delay fall back to a
+// lock-step serial loop with register forwarding.  Only the schedule changes, never the
+// arithmetic of a sample, so the result is identical in all modes.
+#include "common.cuh"
+
+namespace modfx {
+namespace {
+
+constexpr int kTile = 128;          // samples per tile (4 sub-steps x 32 lanes)
+constexpr int kSub = kTile / kWarp; // 4
+constexpr int kLoWin = 512;         // control-rate LFO points staged in shared memory at a time
+
+struct FcArgs {
+    const float* x;
+    float* y;
+    int B, C, N;
+    int Mmin, Mlfo, M;
+    int ring_mask;                  // ring size - 1 (power of two >= M + kTile)
+    // modulation source
+    const float* mod;
+    int mod_has_ch;
+    int n_lo;
+    float up_scale;
+    float sr_lo;
+    const float* lfo_freq;
+    const float* lfo_phase;
+    const int32_t* lfo_shape;
+    const float* lfo_exp;
+    // effect parameters: device array or pre-rounded scalar
+    const float* fb_p;    float fb_s;
+    const float* mdw_p;   float min_delay_s;   // scalar: f32(mdw * Mmin) computed in double
+    const float* width_p; float lfo_delay_s;   // scalar: f32(Mlfo * width) computed in double
+    const float* depth_p; float depth_s;
+    const float* mix_p;   float mix_s; float omm_s;   // scalar: f32(1.0 - mix) computed in double
+    const int32_t* index;
+    int n_items;
+};
+
+enum ModMode { kAudioRate = 0, kControlRate = 1, kDirectLfo = 2 };
+
+struct Coef {
+    float A, D0, fb, depth, mix, omm, Mf;
+    int M, mask;
+};
+
+struct Samp {       // per-sample, per-lane state of the current tile
+    float x, fr, omfr;
+    int kp;         // distance (in samples, 1..M) to the write that filled tap p
+};
+
+__device__ __forceinline__ int kq_of(int kp, int M) { return kp > 1 ? kp - 1 : M; }
+
+// Index arithmetic of fx.py:95-102 for sample n (w = n mod M), in the reference's op order.
+__device__ __forceinline__ void fc_index(float m, int w, const Coef& c, float& fr, float& omfr, int& kp) {
+    const float d = __fadd_rn(__fmul_rn(c.A, m), c.D0);                 // fx.py:98
+    const float t = __fadd_rn(__fsub_rn((float)w, d), c.Mf);            // fx.py:99 (before %)
+    float r;
+    if (t >= 0.0f && t < c.Mf) r = t;                                   // fmod is exact here
+    else if (t >= c.Mf && t < __fadd_rn(c.Mf, c.Mf)) r = __fsub_rn(t, c.Mf);   // Sterbenz: exact
+    else r = torch_remainder(t, c.Mf);
+    const float pf = floorf(r);
+    fr = __fsub_rn(r, pf);                                              // fx.py:100
+    int p = (int)pf;                                                    // fx.py:101
+    p = max(0, min(p, c.M - 1));
+    omfr = __fsub_rn(1.0f, fr);                                         // (1.0 - fraction), fx.py:113
+    kp = w - p;
+    if (kp <= 0) kp += c.M;     // read-before-write: a tap at the write slot is M samples old
+}
+
+// One sample of fx.py:111-118 given the two taps.
+__device__ __forceinline__ void fc_sample(const Samp& s, float vp, float vq, const Coef& c, float& v, float& out) {
+    const float it = __fadd_rn(__fmul_rn(s.fr, vq), __fmul_rn(s.omfr, vp));   // fx.py:113
+    v = __fadd_rn(s.x, __fmul_rn(c.fb, it));                                    // fx.py:114
+    const float o = __fadd_rn(s.x, __fmul_rn(c.depth, it));                     // fx.py:115
+    float r = __fadd_rn(__fmul_rn(c.omm, s.x), __fmul_rn(c.mix, o));            // fx.py:117
+    out = fminf(fmaxf(r, -1.0f), 1.0f);                                         // fx.py:118
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x;
+    const int item = blockIdx.x / a.C;
+    const int ch = blockIdx.x - item * a.C;
+    const int b = a.index ? a.index[item] : item;
+    const int N = a.N;
+
+    float* ring = smem;
+    float* lo = smem + (a.ring_mask + 1);
+
+    Coef c;
+    c.M = a.M;
+    c.Mf = (float)a.M;
+    c.mask = a.ring_mask;
+    c.A = a.width_p ? __fmul_rn((float)a.Mlfo, a.width_p[b]) : a.lfo_delay_s;      // fx.py:98
+    c.D0 = a.mdw_p ? __fmul_rn(a.mdw_p[b], (float)a.Mmin) : a.min_delay_s;          // fx.py:97
+    c.fb = a.fb_p ? a.fb_p[b] : a.fb_s;
+    c.depth = a.depth_p ? a.depth_p[b] : a.depth_s;
+    c.mix = a.mix_p ? a.mix_p[b] : a.mix_s;
+    c.omm = a.mix_p ? __fsub_rn(1.0f, c.mix) : a.omm_s;                             // fx.py:117
+
+    for (int i = lane; i <= a.ring_mask; i += kWarp) ring[i] = 0.0f;                // fx.py:92
+
+    LfoDesc lfo;
+    if (MODE == kDirectLfo || (MODE == kControlRate && a.lfo_freq)) {
+        lfo = make_lfo_desc(a.lfo_freq[b], a.lfo_phase[b], a.lfo_shape[b],
+                            a.lfo_exp ? a.lfo_exp[b] : 1.0f, a.sr_lo);
+    }
+    int lo_base = 0, lo_end = 0;    // control points [lo_base, lo_end) are staged in lo[]
+    __syncwarp();
+
+    const float* xs = a.x + ((int64_t)b * a.C + ch) * (int64_t)N;
+    float* ys = a.y + ((int64_t)b * a.C + ch) * (int64_t)N;
+    const float* ms = nullptr;
+    if (MODE == kAudioRate) ms = a.mod + (a.mod_has_ch ? ((int64_t)b * a.C + ch) : (int64_t)b) * (int64_t)N;
+
+    int w0 = 0;     // n0 mod M
+    for (int n0 = 0; n0 < N; n0 += kTile) {
+        if (MODE == kControlRate) {
+            // Slide the staged window of the control-rate LFO (882 points per 2 s clip in the
+            // reference pipeline) so that it covers every tap this tile interpolates from.
+            const int last_n = min(n0 + kTile - 1, N - 1);
+            const int need_hi = min((int)__fmul_rn(a.up_scale, (float)last_n) + 1, a.n_lo - 1);
+            if (need_hi >= lo_end) {
+                __syncwarp();
+                lo_base = min((int)__fmul_rn(a.up_scale, (float)n0), a.n_lo - 1);
+                lo_end = min(lo_base + kLoWin, a.n_lo);
+                if (a.lfo_freq) {
+                    for (int i = lo_base + lane; i < lo_end; i += kWarp) lo[i - lo_base] = lfo_value(lfo, i);
+                } else {
+                    const float* src = a.mod + (int64_t)b * a.n_lo;
+                    for (int i = lo_base + lane; i < lo_end; i += kWarp) lo[i - lo_base] = src[i];
+                }
+                __syncwarp();
+            }
+        }
+        Samp s[kSub];
+        bool indep = true;
+#pragma unroll
+        for (int k = 0; k < kSub; ++k) {
+            const int n = n0 + k * kWarp + lane;
+            const bool valid = n < N;
+            int w = w0 + k * kWarp + lane;
+            if (w >= c.M) { w -= c.M; if (w >= c.M) w %= c.M; }
+            float m = 0.0f;
+            s[k].x = 0.0f;
+            if (valid) {
+                s[k].x = xs[n];
+                if (MODE == kAudioRate) m = ms[n];
+                else if (MODE == kControlRate) m = upsample_ac(lo - lo_base, a.n_lo, a.up_scale, n);
+                else m = lfo_value(lfo, n);
+            }
+            fc_index(m, w, c, s[k].fr, s[k].omfr, s[k].kp);
+            const int near = max(s[k].kp - 1, 1);          // = min(kp, kq)
+            indep = indep && (!valid || near > k * kWarp + lane);
+        }
+
+        if (__all_sync(kFull, indep)) {
+            // ---- whole tile independent of itself: 128 samples in one shot ----
+            float vp[kSub], vq[kSub];
+#pragma unroll
+            for (int k = 0; k < kSub; ++k) {
+                const int n = n0 + k * kWarp + lane;
+                vp[k] = ring[(n - s[k].kp) & c.mask];
+                vq[k] = ring[(n - kq_of(s[k].kp, c.M)) & c.mask];
+            }
+#pragma unroll
+            for (int k = 0; k < kSub; ++k) {
+                const int n = n0 + k * kWarp + lane;
+                float v, out;
+                fc_sample(s[k], vp[k], vq[k], c, v, out);
+                ring[n & c.mask] = v;
+                if (n < N) ys[n] = out;
+            }
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int k = 0; k < kSub; ++k) {
+                // ---- one 32-sample block, resolved as waves of independent prefixes ----
+                const int nb = n0 + k * kWarp;
+                const int cnt = min(kWarp, N - nb);
+                if (cnt <= 0) break;
+                const Samp me = s[k];
+                const int n = nb + lane;
+                const int near = max(me.kp - 1, 1);
+                float my_out = 0.0f;
+                int done = 0;
+                while (done < cnt) {
+                    // lanes >= done whose dependencies are already in the ring
+                    const bool ready = (lane < done) || (near > lane - done);
+                    const unsigned blocked = ~__ballot_sync(kFull, ready);
+                    int end = blocked ? (__ffs(blocked) - 1) : kWarp;
+                    end = min(end, cnt);
+                    if (end - done >= 3) {
+                        if (lane >= done && lane < end) {
+                            const float vp = ring[(n - me.kp) & c.mask];
+                            const float vq = ring[(n - kq_of(me.kp, c.M)) & c.mask];
+                            float v;
+                            fc_sample(me, vp, vq, c, v, my_out);
+                            ring[n & c.mask] = v;
+                        }
+                        __syncwarp();
+                        done = end;
+                    } else {
+                        // ---- delay of 1-2 samples: lock-step serial run, taps at distance
+                        //      1 and 2 forwarded from registers instead of shared memory ----
+                        const int stop = min(done + 8, cnt);
+                        float p1 = ring[(nb + done - 1) & c.mask];
+                        float p2 = ring[(nb + done - 2) & c.mask];
+                        for (int i = done; i < stop; ++i) {
+                            Samp si;
+                            si.x = __shfl_sync(kFull, me.x, i);
+                            si.fr = __shfl_sync(kFull, me.fr, i);
+                            si.omfr = __shfl_sync(kFull, me.omfr, i);
+                            si.kp = __shfl_sync(kFull, me.kp, i);
+                            const int kq = kq_of(si.kp, c.M);
+                            const int ni = nb + i;
+                            float vp, vq;       // warp-uniform branches: no divergence
+                            if (si.kp <= 2) vp = (si.kp == 1) ? p1 : p2;
+                            else vp = ring[(ni - si.kp) & c.mask];
+                            if (kq <= 2) vq = (kq == 1) ? p1 : p2;
+                            else vq = ring[(ni - kq) & c.mask];
+                            float v, out;
+                            fc_sample(si, vp, vq, c, v, out);
+                            ring[ni & c.mask] = v;      // every lane stores the same value
+                            if (lane == i) my_out = out;
+                            p2 = p1;
+                            p1 = v;
+                        }
+                        __syncwarp();
+                        done = stop;
+                    }
+                }
+                if (lane < cnt) ys[n] = my_out;
+            }
+        }
+        w0 += kTile;
+        if (w0 >= c.M) { w0 -= c.M; if (w0 >= c.M) w0 %= c.M; }
+    }
+}
+
+// apply_tremolo, fx.py:13-22: ((1 - mix) * x) + ((mix * mod) * x); one block per (example, channel).
+template <int MODE>
+__global__ void __launch_bounds__(256) tremolo_kernel(const FcArgs a) {
+    extern __shared__ float smem[];
+    const int b = blockIdx.x / a.C;
+    const int ch = blockIdx.x - b * a.C;
+    const int N = a.N;
+    const float* lo = smem;
+    LfoDesc lfo;
+    if (MODE == kDirectLfo || (MODE == kControlRate && a.lfo_freq))
+        lfo = make_lfo_desc(a.lfo_freq[b], a.lfo_phase[b], a.lfo_shape[b], a.lfo_exp ? a.lfo_exp[b] : 1.0f, a.sr_lo);
+    if (MODE == kControlRate) {
+        if (a.lfo_freq) {       // synthesise the control-rate row once per block
+            for (int i = threadIdx.x; i < a.n_lo; i += blockDim.x) smem[i] = lfo_value(lfo, i);
+            __syncthreads();
+        } else {
+            lo = a.mod + (int64_t)b * a.n_lo;   // elementwise op: the two taps stay in L1
+        }
+    }
+    const float mix = a.mix_p ? a.mix_p[b] : a.mix_s;
+    const float omm = a.mix_p ? __fsub_rn(1.0f, mix) : a.omm_s;
+    const float* xs = a.x + ((int64_t)b * a.C + ch) * (int64_t)N;
+    float* ys = a.y + ((int64_t)b * a.C + ch) * (int64_t)N;
+    const float* ms = nullptr;
+    if (MODE == kAudioRate) ms = a.mod + (a.mod_has_ch ? ((int64_t)b * a.C + ch) : (int64_t)b) * (int64_t)N;
+    for (int n = blockIdx.y * blockDim.x + threadIdx.x; n < N; n += gridDim.y * blockDim.x) {
+        float m;
+        if (MODE == kAudioRate) m = ms[n];
+        else if (MODE == kControlRate) m = upsample_ac(lo, a.n_lo, a.up_scale, n);
+        else m = lfo_value(lfo, n);
+        const float xv = xs[n];
+        ys[n] = __fadd_rn(__fmul_rn(omm, xv), __fmul_rn(__fmul_rn(mix, m), xv));
+    }
+}
+
+int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+int fill_mod(FcArgs& a, const modfx_mod_source* mod, int B, int64_t N, int& mode) {
+    MODFX_REQUIRE(mod != nullptr, "mod source is NULL");
+    a.mod = mod->mod;
+    a.mod_has_ch = mod->mod_has_ch;
+    a.n_lo = 0;
+    a.up_scale = 0.0f;
+    a.sr_lo = mod->sr_lo;
+    a.lfo_freq = nullptr;
+    a.lfo_phase = nullptr;
+    a.lfo_shape = nullptr;
+    a.lfo_exp = nullptr;
+    switch (mod->kind) {
+        case MODFX_MOD_AUDIO_RATE:
+            MODFX_REQUIRE(mod->mod != nullptr, "audio-rate mod pointer is NULL");
+            mode = kAudioRate;
+            break;
+        case MODFX_MOD_CONTROL_RATE:
+            MODFX_REQUIRE(mod->mod != nullptr, "control-rate mod pointer is NULL");
+            MODFX_REQUIRE(mod->n_lo >= 1 && mod->n_lo <= N, "control-rate n_lo=%lld must be in [1, N]",
+                          (long long)mod->n_lo);
+            a.n_lo = (int)mod->n_lo;
+            a.up_scale = upsample_scale_ac(mod->n_lo, N);
+            mode = kControlRate;
+            if (mod->n_lo == N) mode = kAudioRate, a.mod_has_ch = 0;   // util.py:18-19: same length => untouched
+            break;
+        case MODFX_MOD_LFO:
+            MODFX_REQUIRE(mod->lfo_freq && mod->lfo_phase && mod->lfo_shape, "LFO parameter pointer is NULL");
+            MODFX_REQUIRE(mod->sr_lo > 0.0f, "LFO sample rate must be positive");
+            MODFX_REQUIRE(mod->n_lo >= 1, "LFO n_lo must be >= 1");
+            a.lfo_freq = mod->lfo_freq;
+            a.lfo_phase = mod->lfo_phase;
+            a.lfo_shape = mod->lfo_shape;
+            a.lfo_exp = mod->lfo_exp;
+            if (mod->n_lo == N) mode = kDirectLfo;
+            else {
+                MODFX_REQUIRE(mod->n_lo <= N, "LFO n_lo=%lld must be <= N", (long long)mod->n_lo);
+                a.n_lo = (int)mod->n_lo;
+                a.up_scale = upsample_scale_ac(mod->n_lo, N);
+                mode = kControlRate;
+            }
+            break;
+        default:
+            return fail(MODFX_ERR_INVALID, "unknown mod kind %d", mod->kind);
+    }
+    (void)B;
+    return MODFX_OK;
+}
+
+int check_scalar(const modfx_param& p, const char* name, bool can_be_one) {
+    if (p.dev) return MODFX_OK;     // device arrays are range-checked by the caller (fx.py:52-57 needs a sync)
+    // fx.py:65-69
+    MODFX_REQUIRE(p.value >= 0.0, "%s=%g must be >= 0", name, p.value);
+    if (can_be_one) MODFX_REQUIRE(p.value <= 1.0, "%s=%g must be <= 1", name, p.value);
+    else MODFX_REQUIRE(p.value < 1.0, "%s=%g must be < 1", name, p.value);
+    return MODFX_OK;
+}
+
+}  // namespace
+}  // namespace modfx
+
+using namespace modfx;
+
+extern "C" int modfx_flanger_chorus_f32(const float* x, float* y, int32_t B, int32_t C, int64_t N,
+                                        int32_t Mmin, int32_t Mlfo, const modfx_mod_source* mod,
+                                        modfx_param feedback, modfx_param min_delay_width, modfx_param width,
+                                        modfx_param depth, modfx_param mix, const int32_t* example_index,
+                                        int32_t n_items, void* stream) {
+    MODFX_REQUIRE(x && y, "x / y is NULL");
+    MODFX_REQUIRE(B >= 0 && C >= 1 && N >= 1, "bad shape B=%d C=%d N=%lld", B, C, (long long)N);
+    MODFX_REQUIRE(N < (1ll << 30), "N=%lld too long (max 2^30-1 samples)", (long long)N);
+    MODFX_REQUIRE(Mmin >= 0 && Mlfo >= 0 && Mmin + Mlfo >= 1, "bad delay line Mmin=%d Mlfo=%d", Mmin, Mlfo);
+    int st;
+    if ((st = check_scalar(feedback, "feedback", false)) != MODFX_OK) return st;          // fx.py:86
+    if ((st = check_scalar(min_delay_width, "min_delay_width", true)) != MODFX_OK) return st;
+    if ((st = check_scalar(width, "width", true)) != MODFX_OK) return st;
+    if ((st = check_scalar(depth, "depth", true)) != MODFX_OK) return st;
+    if ((st = check_scalar(mix, "mix", true)) != MODFX_OK) return st;
+
+    FcArgs a{};
+    a.x = x; a.y = y; a.B = B; a.C = C; a.N = (int)N;
+    a.Mmin = Mmin; a.Mlfo = Mlfo; a.M = Mmin + Mlfo;
+    int mode = 0;
+    if ((st = fill_mod(a, mod, B, N, mode)) != MODFX_OK) return st;
+    const int ring = next_pow2(a.M + kTile);
+    a.ring_mask = ring - 1;
+    a.fb_p = feedback.dev;         a.fb_s = (float)feedback.value;
+    a.mdw_p = min_delay_width.dev; a.min_delay_s = (float)(min_delay_width.value * (double)Mmin);
+    a.width_p = width.dev;         a.lfo_delay_s = (float)((double)Mlfo * width.value);
+    a.depth_p = depth.dev;         a.depth_s = (float)depth.value;
+    a.mix_p = mix.dev;             a.mix_s = (float)mix.value; a.omm_s = (float)(1.0 - mix.value);
+    a.index = example_index;
+    a.n_items = example_index ? n_items : B;
+    if (a.n_items == 0) return MODFX_OK;
+    MODFX_REQUIRE(a.n_items > 0, "n_items=%d", a.n_items);
+
+    const size_t smem = sizeof(float) * ((size_t)ring + (mode == kControlRate ? (size_t)kLoWin : 0));
+    if (smem > 200 * 1024)
+        return fail(MODFX_ERR_UNSUPPORTED, "delay line of %d samples (+%d control points) needs %zu B of shared memory",
+                    a.M, a.n_lo, smem);
+    const dim3 grid((unsigned)((int64_t)a.n_items * C));
+    cudaStream_t s = as_stream(stream);
+#define LAUNCH_FC(MODE)                                                                                   \
+    do {                                                                                                  \
+        if (smem > 48 * 1024)                                                                             \
+            MODFX_CUDA_OK(cudaFuncSetAttribute(fc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        fc_kernel<MODE><<<grid, kWarp, smem, s>>>(a);                                                     \
+    } while (0)
+    if (mode == kAudioRate) LAUNCH_FC(kAudioRate);
+    else if (mode == kControlRate) LAUNCH_FC(kControlRate);
+    else LAUNCH_FC(kDirectLfo);
+#undef LAUNCH_FC
+    MODFX_CUDA_OK(cudaGetLastError());
+    return MODFX_OK;
+}
+
+extern "C" int modfx_tremolo_f32(const float* x, float* y, int32_t B, int32_t C, int64_t N,
+                                 const modfx_mod_source* mod, modfx_param mix, void* stream) {
+    MODFX_REQUIRE(x && y, "x / y is NULL");
+    MODFX_REQUIRE(B >= 0 && C >= 1 && N >= 1 && N < (1ll << 30), "bad shape B=%d C=%d N=%lld", B, C, (long long)N);
+    int st;
+    if ((st = check_scalar(mix, "mix", true)) != MODFX_OK) return st;                     // fx.py:21
+    FcArgs a{};
+    a.x = x; a.y = y; a.B = B; a.C = C; a.N = (int)N;
+    int mode = 0;
+    if ((st = fill_mod(a, mod, B, N, mode)) != MODFX_OK) return st;
+    a.mix_p = mix.dev; a.mix_s = (float)mix.value; a.omm_s = (float)(1.0 - mix.value);
+    if (B == 0) return MODFX_OK;
+    const size_t smem = sizeof(float) * ((mode == kControlRate && a.lfo_freq) ? (size_t)a.n_lo : 0);
+    if (smem > 200 * 1024)
+        return fail(MODFX_ERR_UNSUPPORTED, "tremolo with an in-kernel control-rate LFO of %d points exceeds shared memory", a.n_lo);
+    int ny = (int)((N + 256 * 8 - 1) / (256 * 8));
+    if (ny < 1) ny = 1;
+    if (ny > 65535) ny = 65535;
+    const dim3 grid((unsigned)(B * C), (unsigned)ny);
+    cudaStream_t s = as_stream(stream);
+#define LAUNCH_TR(MODE)                                                                                   \
+    do {                                                                                                  \
+        if (smem > 48 * 1024)                                                                             \
+            MODFX_CUDA_OK(cudaFuncSetAttribute(tremolo_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        tremolo_kernel<MODE><<<grid, 256, smem, s>>>(a);                                                  \
+    } while (0)
+    if (mode == kAudioRate) LAUNCH_TR(kAudioRate);
+    else if (mode == kControlRate) LAUNCH_TR(kControlRate);
+    else LAUNCH_TR(kDirectLfo);
+#undef LAUNCH_TR
+    MODFX_CUDA_OK(cudaGetLastError());
+    return MODFX_OK;
+}
