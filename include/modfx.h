@@ -123,12 +123,15 @@ int modfx_interp_linear_f32(const float* in, float* out, int64_t rows, int64_t I
  *   window    (n_fft,) device
  *   fb_start, fb_count (n_mels,) int32 device: first FFT bin and number of taps of each mel band
  *   fb_weight (n_mels, fb_stride) float32 device: tap weights, zero padded
- * Supported: n_fft == 1024, hop == 256.
+ *   apply_log 1: out = log(max(mel, eps)) (models.py:207-208); 0: out = mel power, which is what
+ *             the `spectrogram` attribute itself returns (SpecAugment sits between the two in
+ *             training, models.py:201-205)
+ * Supported: n_fft == 1024, even hop in [2, 512].
  */
 int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T, int32_t n_fft, int32_t hop,
                      int32_t n_mels, const float* window, const int32_t* fb_start,
                      const int32_t* fb_count, const float* fb_weight, int32_t fb_stride, float eps,
-                     void* stream);
+                     int32_t apply_log, void* stream);
 
 /*
  * Replaces PedalboardPhaserDataset.apply_pedalboard_phaser's DSP, mod_extraction/datasets.py:455-482

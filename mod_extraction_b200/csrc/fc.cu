@@ -21,6 +21,8 @@ namespace {
 constexpr int kTile = 128;          // samples per tile (4 sub-steps x 32 lanes)
 constexpr int kSub = kTile / kWarp; // 4
 constexpr int kLoWin = 512;         // control-rate LFO points staged in shared memory at a time
+constexpr int kStages = 8;          // dry-audio tiles in flight per warp (cp.async ring)
+constexpr int kMinWave = 6;         // below this dependency distance a block runs serially
 
 struct FcArgs {
     const float* x;
@@ -88,17 +90,50 @@ __device__ __forceinline__ void fc_sample(const Samp& s, float vp, float vq, con
     out = fminf(fmaxf(r, -1.0f), 1.0f);                                         // fx.py:118
 }
 
+// ---- cp.async staging of the dry audio (and the audio-rate mod_sig) ---------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Stage samples [n0, n0 + kTile) of `row` into `dst` (zero-filled past N).
+__device__ __forceinline__ void stage_tile(float* dst, const float* row, int n0, int N, int lane, bool vec16) {
+    if (n0 >= N) return;
+    if (vec16) {
+        const int n = n0 + 4 * lane;
+        if (n < N) cp_async_16(dst + 4 * lane, row + n, min(16, (N - n) * 4));
+        else *reinterpret_cast<float4*>(dst + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kSub; ++k) {
+            const int n = n0 + k * kWarp + lane;
+            if (n < N) cp_async_4(dst + k * kWarp + lane, row + n, 4);
+            else dst[k * kWarp + lane] = 0.0f;
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x;
     const int item = blockIdx.x / a.C;
     const int ch = blockIdx.x - item * a.C;
     const int b = a.index ? a.index[item] : item;
     const int N = a.N;
 
-    float* ring = smem;
-    float* lo = smem + (a.ring_mask + 1);
+    // shared memory: [x stages][mod stages (audio-rate) | LFO window (control-rate)][ring]
+    float* xst = smem;
+    float* mst = smem + kStages * kTile;
+    float* lo = mst;
+    float* ring = smem + kStages * kTile + ((MODE == kAudioRate) ? kStages * kTile : ((MODE == kControlRate) ? kLoWin : 0));
 
     Coef c;
     c.M = a.M;
@@ -111,6 +146,21 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
     c.mix = a.mix_p ? a.mix_p[b] : a.mix_s;
     c.omm = a.mix_p ? __fsub_rn(1.0f, c.mix) : a.omm_s;                             // fx.py:117
 
+    const float* xs = a.x + ((int64_t)b * a.C + ch) * (int64_t)N;
+    float* ys = a.y + ((int64_t)b * a.C + ch) * (int64_t)N;
+    const float* ms = nullptr;
+    if (MODE == kAudioRate) ms = a.mod + (a.mod_has_ch ? ((int64_t)b * a.C + ch) : (int64_t)b) * (int64_t)N;
+    const bool xvec = (((uintptr_t)xs) & 15) == 0;
+    const bool mvec = (MODE == kAudioRate) && ((((uintptr_t)ms) & 15) == 0);
+
+    // prologue of the copy pipeline: tiles 0 .. kStages-2
+#pragma unroll
+    for (int t = 0; t < kStages - 1; ++t) {
+        stage_tile(xst + t * kTile, xs, t * kTile, N, lane, xvec);
+        if (MODE == kAudioRate) stage_tile(mst + t * kTile, ms, t * kTile, N, lane, mvec);
+        cp_async_commit();
+    }
+
     for (int i = lane; i <= a.ring_mask; i += kWarp) ring[i] = 0.0f;                // fx.py:92
 
     LfoDesc lfo;
@@ -121,13 +171,17 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
     int lo_base = 0, lo_end = 0;    // control points [lo_base, lo_end) are staged in lo[]
     __syncwarp();
 
-    const float* xs = a.x + ((int64_t)b * a.C + ch) * (int64_t)N;
-    float* ys = a.y + ((int64_t)b * a.C + ch) * (int64_t)N;
-    const float* ms = nullptr;
-    if (MODE == kAudioRate) ms = a.mod + (a.mod_has_ch ? ((int64_t)b * a.C + ch) : (int64_t)b) * (int64_t)N;
-
     int w0 = 0;     // n0 mod M
+    int stage = 0;  // tile index mod kStages
     for (int n0 = 0; n0 < N; n0 += kTile) {
+        {   // keep kStages-1 tiles of dry audio in flight
+            int ps = stage + kStages - 1;
+            if (ps >= kStages) ps -= kStages;
+            const int pn = n0 + (kStages - 1) * kTile;
+            stage_tile(xst + ps * kTile, xs, pn, N, lane, xvec);
+            if (MODE == kAudioRate) stage_tile(mst + ps * kTile, ms, pn, N, lane, mvec);
+            cp_async_commit();
+        }
         if (MODE == kControlRate) {
             // Slide the staged window of the control-rate LFO (882 points per 2 s clip in the
             // reference pipeline) so that it covers every tap this tile interpolates from.
@@ -143,28 +197,30 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
                     const float* src = a.mod + (int64_t)b * a.n_lo;
                     for (int i = lo_base + lane; i < lo_end; i += kWarp) lo[i - lo_base] = src[i];
                 }
-                __syncwarp();
             }
         }
+        cp_async_wait<kStages - 1>();       // this tile's copies (issued kStages-1 tiles ago) landed
+        __syncwarp();
+
+        const float* xt = xst + stage * kTile;
+        const float* mt = mst + stage * kTile;
         Samp s[kSub];
         bool indep = true;
 #pragma unroll
         for (int k = 0; k < kSub; ++k) {
-            const int n = n0 + k * kWarp + lane;
+            const int j = k * kWarp + lane;
+            const int n = n0 + j;
             const bool valid = n < N;
-            int w = w0 + k * kWarp + lane;
+            int w = w0 + j;
             if (w >= c.M) { w -= c.M; if (w >= c.M) w %= c.M; }
-            float m = 0.0f;
-            s[k].x = 0.0f;
-            if (valid) {
-                s[k].x = xs[n];
-                if (MODE == kAudioRate) m = ms[n];
-                else if (MODE == kControlRate) m = upsample_ac(lo - lo_base, a.n_lo, a.up_scale, n);
-                else m = lfo_value(lfo, n);
-            }
+            float m;
+            s[k].x = xt[j];
+            if (MODE == kAudioRate) m = mt[j];
+            else if (MODE == kControlRate) m = upsample_ac(lo - lo_base, a.n_lo, a.up_scale, min(n, N - 1));
+            else m = valid ? lfo_value(lfo, n) : 0.0f;
             fc_index(m, w, c, s[k].fr, s[k].omfr, s[k].kp);
             const int near = max(s[k].kp - 1, 1);          // = min(kp, kq)
-            indep = indep && (!valid || near > k * kWarp + lane);
+            indep = indep && (!valid || near > j);
         }
 
         if (__all_sync(kFull, indep)) {
@@ -184,27 +240,32 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
                 ring[n & c.mask] = v;
                 if (n < N) ys[n] = out;
             }
-            __syncwarp();
         } else {
 #pragma unroll
             for (int k = 0; k < kSub; ++k) {
-                // ---- one 32-sample block, resolved as waves of independent prefixes ----
+                // ---- one 32-sample block ----
                 const int nb = n0 + k * kWarp;
                 const int cnt = min(kWarp, N - nb);
                 if (cnt <= 0) break;
                 const Samp me = s[k];
                 const int n = nb + lane;
-                const int near = max(me.kp - 1, 1);
+                const int near = (lane < cnt) ? max(me.kp - 1, 1) : 0x7fffffff;
+                // smallest dependency distance relative to the block start, over the block
+                const int slack = __reduce_min_sync(kFull, (lane < cnt) ? (near - lane) : 0x7fffffff);
+                const int mn = __reduce_min_sync(kFull, near);
                 float my_out = 0.0f;
-                int done = 0;
-                while (done < cnt) {
-                    // lanes >= done whose dependencies are already in the ring
-                    const bool ready = (lane < done) || (near > lane - done);
-                    const unsigned blocked = ~__ballot_sync(kFull, ready);
-                    int end = blocked ? (__ffs(blocked) - 1) : kWarp;
-                    end = min(end, cnt);
-                    if (end - done >= 3) {
-                        if (lane >= done && lane < end) {
+                if (slack > 0) {
+                    // every sample depends only on samples before the block: one wave
+                    const float vp = ring[(n - me.kp) & c.mask];
+                    const float vq = ring[(n - kq_of(me.kp, c.M)) & c.mask];
+                    float v;
+                    fc_sample(me, vp, vq, c, v, my_out);
+                    __syncwarp();
+                    if (lane < cnt) ring[n & c.mask] = v;
+                } else if (mn >= kMinWave) {
+                    // waves of mn consecutive samples: sample j depends on samples <= j - mn
+                    for (int done = 0; done < cnt; done += mn) {
+                        if (lane >= done && lane < done + mn && lane < cnt) {
                             const float vp = ring[(n - me.kp) & c.mask];
                             const float vq = ring[(n - kq_of(me.kp, c.M)) & c.mask];
                             float v;
@@ -212,43 +273,57 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
                             ring[n & c.mask] = v;
                         }
                         __syncwarp();
-                        done = end;
-                    } else {
-                        // ---- delay of 1-2 samples: lock-step serial run, taps at distance
-                        //      1 and 2 forwarded from registers instead of shared memory ----
-                        const int stop = min(done + 8, cnt);
-                        float p1 = ring[(nb + done - 1) & c.mask];
-                        float p2 = ring[(nb + done - 2) & c.mask];
-                        for (int i = done; i < stop; ++i) {
-                            Samp si;
-                            si.x = __shfl_sync(kFull, me.x, i);
-                            si.fr = __shfl_sync(kFull, me.fr, i);
-                            si.omfr = __shfl_sync(kFull, me.omfr, i);
-                            si.kp = __shfl_sync(kFull, me.kp, i);
-                            const int kq = kq_of(si.kp, c.M);
-                            const int ni = nb + i;
-                            float vp, vq;       // warp-uniform branches: no divergence
-                            if (si.kp <= 2) vp = (si.kp == 1) ? p1 : p2;
-                            else vp = ring[(ni - si.kp) & c.mask];
-                            if (kq <= 2) vq = (kq == 1) ? p1 : p2;
-                            else vq = ring[(ni - kq) & c.mask];
-                            float v, out;
-                            fc_sample(si, vp, vq, c, v, out);
-                            ring[ni & c.mask] = v;      // every lane stores the same value
-                            if (lane == i) my_out = out;
-                            p2 = p1;
-                            p1 = v;
-                        }
-                        __syncwarp();
-                        done = stop;
+                    }
+                } else {
+                    // ---- delays of a few samples: lock-step serial run over the block.  All
+                    // lanes compute every sample (no divergence); taps at distance 1 and 2 are
+                    // forwarded from registers, older taps are loaded two samples ahead so the
+                    // shared-memory latency stays off the recurrence's critical path. ----
+                    float p1 = ring[(nb - 1) & c.mask];
+                    float p2 = ring[(nb - 2) & c.mask];
+                    int kpa = __shfl_sync(kFull, me.kp, 0);
+                    int kpb = __shfl_sync(kFull, me.kp, 1);
+                    float lpa = ring[(nb - kpa) & c.mask];
+                    float lqa = ring[(nb - kq_of(kpa, c.M)) & c.mask];
+                    float lpb = ring[(nb + 1 - kpb) & c.mask];
+                    float lqb = ring[(nb + 1 - kq_of(kpb, c.M)) & c.mask];
+                    float my_it = 0.0f;
+#pragma unroll 4
+                    for (int i = 0; i < cnt; ++i) {
+                        // taps of sample i+2 (valid when their distance is >= 3: already stored)
+                        const int kpc = __shfl_sync(kFull, me.kp, (i + 2) & 31);
+                        const float lpc = ring[(nb + i + 2 - kpc) & c.mask];
+                        const float lqc = ring[(nb + i + 2 - kq_of(kpc, c.M)) & c.mask];
+                        const float xi = __shfl_sync(kFull, me.x, i);
+                        const float fri = __shfl_sync(kFull, me.fr, i);
+                        const float omi = __shfl_sync(kFull, me.omfr, i);
+                        const int kqa = kq_of(kpa, c.M);
+                        const float vp = (kpa == 1) ? p1 : ((kpa == 2) ? p2 : lpa);
+                        const float vq = (kqa == 1) ? p1 : ((kqa == 2) ? p2 : lqa);
+                        const float it = __fadd_rn(__fmul_rn(fri, vq), __fmul_rn(omi, vp));     // fx.py:113
+                        const float v = __fadd_rn(xi, __fmul_rn(c.fb, it));                      // fx.py:114
+                        ring[(nb + i) & c.mask] = v;        // every lane stores the same value
+                        if (lane == i) my_it = it;
+                        p2 = p1; p1 = v;
+                        kpa = kpb; lpa = lpb; lqa = lqb;
+                        kpb = kpc; lpb = lpc; lqb = lqc;
+                    }
+                    {   // per-lane output of fx.py:115-118 from the stored interpolated value
+                        const float o = __fadd_rn(me.x, __fmul_rn(c.depth, my_it));
+                        const float r = __fadd_rn(__fmul_rn(c.omm, me.x), __fmul_rn(c.mix, o));
+                        my_out = fminf(fmaxf(r, -1.0f), 1.0f);
                     }
                 }
                 if (lane < cnt) ys[n] = my_out;
+                __syncwarp();
             }
         }
+        __syncwarp();
         w0 += kTile;
         if (w0 >= c.M) { w0 -= c.M; if (w0 >= c.M) w0 %= c.M; }
+        if (++stage == kStages) stage = 0;
     }
+    cp_async_wait<0>();
 }
 
 // apply_tremolo, fx.py:13-22: ((1 - mix) * x) + ((mix * mod) * x); one block per (example, channel).
@@ -387,7 +462,8 @@ extern "C" int modfx_flanger_chorus_f32(const float* x, float* y, int32_t B, int
     if (a.n_items == 0) return MODFX_OK;
     MODFX_REQUIRE(a.n_items > 0, "n_items=%d", a.n_items);
 
-    const size_t smem = sizeof(float) * ((size_t)ring + (mode == kControlRate ? (size_t)kLoWin : 0));
+    const size_t smem = sizeof(float) * ((size_t)ring + (size_t)kStages * kTile +
+                                         (mode == kAudioRate ? (size_t)kStages * kTile : (mode == kControlRate ? (size_t)kLoWin : 0)));
     if (smem > 200 * 1024)
         return fail(MODFX_ERR_UNSUPPORTED, "delay line of %d samples (+%d control points) needs %zu B of shared memory",
                     a.M, a.n_lo, smem);

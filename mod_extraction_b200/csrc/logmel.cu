@@ -1,7 +1,213 @@
-// placeholder until the FFT kernel lands (next commit)
+// Log-mel front end of the lfo_2dcnn extractor, fused into one kernel:
+//   reflect-pad -> frame -> periodic Hann -> 1024-point real FFT -> |.|^2 -> banded mel -> clip -> log
+// Replaces Spectral2DCNN.spectrogram (torchaudio MelSpectrogram) + tr.clip + tr.log, reference
+// mod_extraction/models.py:170-175,199,207-208.
+//
+// Why no tensor cores (DESIGN.md "M1"): a dense DFT is 17x the flops of the FFT and needs 3xTF32 or
+// 6xBF16 error compensation to hold the 1e-4 log-mel tolerance; the mel matrix is 0.77 % dense.
+// Both are not "genuine dense contractions", so the FFT runs in registers on the FP32 pipes
+// (fft_core.h) and the mel projection is a <=14-tap banded sum.
+//
+// Work split: one CTA of 4 warps owns a row (example x channel) and a range of frames and walks it
+// 8 frames at a time: the audio span of the 8 frames is staged once in shared memory (each sample
+// is read from HBM once per CTA although it belongs to 4 frames), every warp transforms two frames,
+// the 8 power spectra meet in shared memory and the mel/log stage writes 8 consecutive frames of
+// every mel row (32 B segments of the (R, n_mels, n_frames) output).
 #include "common.cuh"
+#include "fft_core.h"
+
+namespace modfx {
+namespace {
+
+constexpr int kNfft = 1024;
+constexpr int kBins = kNfft / 2 + 1;     // 513
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * kWarp;
+constexpr int kFB = 2 * kWarps;          // frames per CTA iteration
+constexpr int kPStride = kFB + 1;        // padded row of the power matrix P[bin][frame]
+constexpr int kEStride = 33;             // padded row of the pass-1 -> pass-2 exchange buffer
+
+struct LogMelArgs {
+    const float* x;
+    float* out;
+    int64_t R, T;
+    int hop, n_mels, n_frames;
+    const float* window;
+    const int32_t* fb_start;
+    const int32_t* fb_count;
+    const float* fb_weight;
+    int fb_stride;
+    float eps;
+    int apply_log;
+    int chunks;          // CTAs per row
+    int iters_per_chunk; // iterations (of kFB frames) per CTA
+};
+
+__device__ __forceinline__ int reflect_index(int i, int T) {
+    // torch.nn.functional.pad(mode="reflect"): -1 -> 1, T -> T-2
+    if (i < 0) i = -i;
+    if (i >= T) i = 2 * (T - 1) - i;
+    return max(0, min(i, T - 1));      // frames past the end of a short clip are computed but never stored
+}
+
+__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogMelArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int64_t row = blockIdx.x / a.chunks;
+    const int chunk = blockIdx.x - (int)row * a.chunks;
+    const int T = (int)a.T;
+    const int span = (kFB - 1) * a.hop + kNfft;      // samples staged per iteration
+
+    float* win = smem;                         // [1024]
+    float* tw1c = win + kNfft;                 // [16][32]  cos(-2 pi n2 k1 / 512)
+    float* tw1s = tw1c + 512;
+    float* tw2c = tw1s + 512;                  // [512]     cos(2 pi k / 1024)
+    float* tw2s = tw2c + 512;
+    float* P = tw2s + 512;                     // [513][kPStride]
+    float* E = P + kBins * kPStride + 3;       // per warp: Er[32][33], Ei[32][33]
+    E = E - ((E - smem) & 3);                  // keep 16-byte alignment
+    float* Er = E + warp * (2 * 32 * kEStride);
+    float* Ei = Er + 32 * kEStride;
+    float* sbuf = E + kWarps * (2 * 32 * kEStride);   // [span]
+
+    for (int i = tid; i < kNfft; i += kThreads) win[i] = a.window[i];
+    for (int i = tid; i < 512; i += kThreads) {
+        const int k1 = i >> 5, n2 = i & 31;
+        float s, c;
+        sincospif(-(float)(n2 * k1) / 256.0f, &s, &c);
+        tw1c[i] = c;
+        tw1s[i] = s;
+        sincospif((float)i / 512.0f, &s, &c);
+        tw2c[i] = c;
+        tw2s[i] = s;
+    }
+
+    const float* xr = a.x + row * a.T;
+    float* orow = a.out + row * (int64_t)a.n_mels * a.n_frames;
+    const int it_begin = chunk * a.iters_per_chunk;
+    const int it_end = min(it_begin + a.iters_per_chunk, (a.n_frames + kFB - 1) / kFB);
+
+    for (int it = it_begin; it < it_end; ++it) {
+        const int t0 = it * kFB;
+        // ---- stage the audio span of frames t0 .. t0+7 (center=True: frame t starts at t*hop - 512)
+        const int s0 = t0 * a.hop - kNfft / 2;
+        for (int i = tid; i < span; i += kThreads) sbuf[i] = xr[reflect_index(s0 + i, T)];
+        __syncthreads();
+
+        const int lf = 2 * warp;                        // local index of this warp's first frame
+        if (t0 + lf < a.n_frames) {
+            // ---- pass 1: lane = n2; 16-point FFT over n1 of z[32 n1 + n2], both frames
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                float re[16], im[16];
+                const float* fr = sbuf + (lf + f) * a.hop;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const float2 v = *reinterpret_cast<const float2*>(fr + 64 * n1 + 2 * lane);
+                    const float2 w = *reinterpret_cast<const float2*>(win + 64 * n1 + 2 * lane);
+                    re[n1] = v.x * w.x;
+                    im[n1] = v.y * w.y;
+                }
+                fft_dif<16>(re, im);
+#pragma unroll
+                for (int k1 = 0; k1 < 16; ++k1) {
+                    const float yr = re[BitRev<16>::of(k1)], yi = im[BitRev<16>::of(k1)];
+                    const float c = tw1c[k1 * 32 + lane], s = tw1s[k1 * 32 + lane];
+                    Er[(f * 16 + k1) * kEStride + lane] = yr * c - yi * s;
+                    Ei[(f * 16 + k1) * kEStride + lane] = yr * s + yi * c;
+                }
+            }
+            __syncwarp();
+            // ---- pass 2: lane = (frame f, k1); 32-point FFT over n2
+            float re[32], im[32];
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) {
+                re[n2] = Er[lane * kEStride + n2];
+                im[n2] = Ei[lane * kEStride + n2];
+            }
+            fft_dif<32>(re, im);
+            // ---- real-FFT split + power: this lane owns bins k = k1 + 16 k2 of its frame
+            const int f = lane >> 4, k1 = lane & 15;
+            const int partner = (lane & 16) | ((16 - k1) & 15);
+            float* Pcol = P + (lf + f);
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) {
+                const int own = BitRev<32>::of(k2);
+                const int src_other = BitRev<32>::of(31 - k2);          // Z[512-k] lives in the partner lane
+                const int src_self = BitRev<32>::of((32 - k2) & 31);    // ... or in this lane when k1 == 0
+                float pr = __shfl_sync(kFull, re[src_other], partner);
+                float pi = __shfl_sync(kFull, im[src_other], partner);
+                if (k1 == 0) {
+                    pr = re[src_self];
+                    pi = im[src_self];
+                }
+                const int k = k1 + 16 * k2;
+                Pcol[k * kPStride] = rfft_split_power(re[own], im[own], pr, pi, tw2c[k], tw2s[k]);
+            }
+            if (k1 == 0) {
+                const float v = re[0] - im[0];          // X[512] = Re Z[0] - Im Z[0]
+                Pcol[512 * kPStride] = v * v;
+            }
+        }
+        __syncthreads();
+
+        // ---- banded mel projection + clip + log; thread = (frame t, mel group)
+        {
+            const int t = tid & (kFB - 1);
+            const int mg = tid / kFB;                   // 0 .. kThreads/kFB - 1
+            const bool live = (t0 + t) < a.n_frames;
+            for (int m = mg; m < a.n_mels; m += kThreads / kFB) {
+                const int start = __ldg(a.fb_start + m);
+                const int cnt = __ldg(a.fb_count + m);
+                const float* w = a.fb_weight + (int64_t)m * a.fb_stride;
+                float acc = 0.0f;
+                for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(w + j), P[(start + j) * kPStride + t], acc);
+                if (live) orow[(int64_t)m * a.n_frames + t0 + t] = a.apply_log ? logf(fmaxf(acc, a.eps)) : acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+}  // namespace modfx
+
 using namespace modfx;
-extern "C" int modfx_logmel_f32(const float*, float*, int64_t, int64_t, int32_t, int32_t, int32_t, const float*,
-                                const int32_t*, const int32_t*, const float*, int32_t, float, void*) {
-    return fail(MODFX_ERR_UNSUPPORTED, "log-mel kernel not built yet");
+
+extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T, int32_t n_fft, int32_t hop,
+                                int32_t n_mels, const float* window, const int32_t* fb_start,
+                                const int32_t* fb_count, const float* fb_weight, int32_t fb_stride, float eps,
+                                int32_t apply_log, void* stream) {
+    MODFX_REQUIRE(x && out && window && fb_start && fb_count && fb_weight, "NULL pointer");
+    MODFX_REQUIRE(R >= 0 && T >= 1, "bad shape R=%lld T=%lld", (long long)R, (long long)T);
+    if (n_fft != kNfft) return fail(MODFX_ERR_UNSUPPORTED, "n_fft=%d (only 1024 is built)", n_fft);
+    if (hop < 2 || hop > 512 || (hop & 1))
+        return fail(MODFX_ERR_UNSUPPORTED, "hop=%d (even hops in [2, 512] are built)", hop);
+    MODFX_REQUIRE(T > n_fft / 2, "reflect padding needs T > n_fft/2 (T=%lld)", (long long)T);   // torch raises too
+    MODFX_REQUIRE(T < (1ll << 30), "T too long");
+    MODFX_REQUIRE(n_mels >= 1 && fb_stride >= 1, "bad mel table");
+    if (R == 0) return MODFX_OK;
+    LogMelArgs a{};
+    a.x = x; a.out = out; a.R = R; a.T = T; a.hop = hop; a.n_mels = n_mels;
+    a.n_frames = (int)(T / hop) + 1;
+    a.window = window; a.fb_start = fb_start; a.fb_count = fb_count; a.fb_weight = fb_weight;
+    a.fb_stride = fb_stride; a.eps = eps; a.apply_log = apply_log;
+    const int iters = (a.n_frames + kFB - 1) / kFB;
+    // enough CTAs to fill the chip twice over even for a handful of rows
+    int chunks = 1;
+    const int64_t want = 4ll * num_sms();
+    if (R < want) chunks = (int)((want + R - 1) / R);
+    if (chunks > iters) chunks = iters;
+    a.iters_per_chunk = (iters + chunks - 1) / chunks;
+    a.chunks = (iters + a.iters_per_chunk - 1) / a.iters_per_chunk;
+    MODFX_REQUIRE(R * a.chunks < (1ll << 31), "grid too large");
+    const int span = (kFB - 1) * hop + kNfft;
+    const size_t smem = sizeof(float) * (size_t)(kNfft + 4 * 512 + kBins * kPStride + 8 +
+                                                 kWarps * 2 * 32 * kEStride + span);
+    MODFX_CUDA_OK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    logmel_kernel<<<(unsigned)(R * a.chunks), kThreads, smem, as_stream(stream)>>>(a);
+    MODFX_CUDA_OK(cudaGetLastError());
+    return MODFX_OK;
 }
