@@ -176,3 +176,38 @@ def interp_linear(x: Tensor, n: int, align_corners: bool = True) -> Tensor:
         _lib.check(_lib.lib().modfx_interp_linear_f32(_ptr(x), _ptr(out), rows, I, n, 1 if align_corners else 0,
                                                       _stream()))
     return out
+
+
+def phaser(x: Tensor, sr: float, rate_hz: Tensor, depth: Tensor, centre_hz: Tensor, feedback: Tensor, mix: Tensor,
+           block: int = 8192, example_index: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """x: (B, N) CUDA float32; per-example (B,) parameters."""
+    _require_cuda(x, "x")
+    assert x.ndim == 2
+    x = x.contiguous()
+    B, N = x.shape
+    y = torch.empty_like(x) if out is None else out
+    assert y.is_cuda and y.is_contiguous() and y.shape == x.shape and y.dtype == torch.float32
+    keep = _Keep()
+    with torch.cuda.device(x.device):
+        ps = []
+        for p, name in ((rate_hz, "rate_hz"), (depth, "depth"), (centre_hz, "centre_frequency_hz"),
+                        (feedback, "feedback"), (mix, "mix")):
+            t = keep(torch.as_tensor(p).detach().to(device=x.device, dtype=torch.float32).reshape(-1).contiguous())
+            if t.numel() == 1 and B != 1:
+                t = keep(t.expand(B).contiguous())
+            assert t.shape == (B,), f"{name}: expected ({B},)"
+            ps.append(t)
+        idx_ptr, n_items = ctypes.c_void_p(0), 0
+        n_work = B
+        if example_index is not None:
+            idx = keep(example_index.to(device=x.device, dtype=torch.int32).contiguous())
+            idx_ptr, n_items = ctypes.c_void_p(idx.data_ptr()), idx.numel()
+            n_work = n_items
+            if n_items == 0:
+                return y
+        L = _lib.lib()
+        ws = keep(torch.empty((max(1, int(L.modfx_phaser_workspace_bytes(n_work, N))),), device=x.device,
+                              dtype=torch.uint8))
+        _lib.check(L.modfx_phaser_f32(_ptr(x), _ptr(y), B, N, float(sr), *[_ptr(t) for t in ps], int(block),
+                                      idx_ptr, n_items, _ptr(ws), _stream()))
+    return y

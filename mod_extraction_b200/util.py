@@ -56,4 +56,4 @@ def sample_log_uniform(low: float, high: float, n: int = 1) -> Union[float, T]:
         return low if n == 1 else tr.full(size=(n,), fill_value=low)
     from scipy.stats import loguniform
     x = loguniform.rvs(low, high, size=n)
-    return float(x) if n == 1 else tr.from_numpy(x)
+    return float(x[0]) if n == 1 else tr.from_numpy(x)
