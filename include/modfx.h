@@ -116,6 +116,31 @@ int modfx_interp_linear_f32(const float* in, float* out, int64_t rows, int64_t I
                             int32_t align_corners, void* stream);
 
 /*
+ * Control-rate pieces of the RNG-driven LFO variants.  The random draws and the integer section
+ * bookkeeping stay with the caller (torch global CPU generator, reference util.py:32-49); the
+ * float32 arithmetic of the reference runs here.
+ *
+ * modfx_find_corners_f32      replaces find_corners, modulations.py:219-238:
+ *                             mod (rows, n) -> top / bottom (rows, n) uint8 flags.
+ * modfx_lfo_sections_f32      replaces the overwrite loop of make_combined_mod_sig,
+ *                             modulations.py:203-209: sections [sec_off[b], sec_off[b+1]) of example b
+ *                             overwrite out[b, start : start+len) with
+ *                             make_mod_signal(len, len, 1.0, 0.0, shape); later sections win.
+ * modfx_stretch_sections_f32  replaces the section stretching + concatenation of make_quasi_periodic,
+ *                             modulations.py:139-159: out[b, out_start[s] ...) = first points of
+ *                             linear_interpolate_last_dim(in[b, in_start : in_start+in_len], new_len);
+ *                             an example without sections is copied unchanged.
+ */
+int modfx_find_corners_f32(const float* mod, uint8_t* top, uint8_t* bottom, int64_t rows, int64_t n,
+                           void* stream);
+int modfx_lfo_sections_f32(float* out, int32_t B, int64_t n, const int32_t* sec_off,
+                           const int32_t* sec_start, const int32_t* sec_len, const int32_t* sec_shape,
+                           void* stream);
+int modfx_stretch_sections_f32(const float* in, float* out, int32_t B, int64_t n, const int32_t* sec_off,
+                               const int32_t* in_start, const int32_t* in_len, const int32_t* new_len,
+                               const int32_t* out_start, void* stream);
+
+/*
  * Replaces Spectral2DCNN.spectrogram + clip + log, mod_extraction/models.py:170-175,199,207-208
  * (torchaudio MelSpectrogram n_fft=1024, hop 256, center/reflect, periodic Hann, power 2).
  *   x         (R, T) rows = batch*channels

@@ -211,3 +211,44 @@ def phaser(x: Tensor, sr: float, rate_hz: Tensor, depth: Tensor, centre_hz: Tens
         _lib.check(L.modfx_phaser_f32(_ptr(x), _ptr(y), B, N, float(sr), *[_ptr(t) for t in ps], int(block),
                                       idx_ptr, n_items, _ptr(ws), _stream()))
     return y
+
+
+def find_corners(mod_sig: Tensor):
+    """(rows, n) CUDA float32 -> (top, bottom) uint8 flags (modulations.py:219-238)."""
+    _require_cuda(mod_sig, "mod_sig")
+    assert mod_sig.ndim == 2
+    m = mod_sig.contiguous()
+    top = torch.empty(m.shape, device=m.device, dtype=torch.uint8)
+    bottom = torch.empty(m.shape, device=m.device, dtype=torch.uint8)
+    with torch.cuda.device(m.device):
+        _lib.check(_lib.lib().modfx_find_corners_f32(_ptr(m), _ptr(top), _ptr(bottom), m.size(0), m.size(1), _stream()))
+    return top, bottom
+
+
+def _i32(values, device) -> Tensor:
+    return torch.tensor(values, dtype=torch.int32).to(device, non_blocking=True)
+
+
+def lfo_sections_(out: Tensor, sec_off, sec_start, sec_len, sec_shape) -> Tensor:
+    """In place: overwrite sections of `out` (B, n) with one-period LFOs (modulations.py:203-209)."""
+    _require_cuda(out, "out")
+    assert out.ndim == 2 and out.is_contiguous()
+    dev = out.device
+    ts = [_i32(v, dev) for v in (sec_off, sec_start, sec_len, sec_shape)]
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().modfx_lfo_sections_f32(_ptr(out), out.size(0), out.size(1), *[_ptr(t) for t in ts],
+                                                     _stream()))
+    return out
+
+
+def stretch_sections(x: Tensor, sec_off, in_start, in_len, new_len, out_start) -> Tensor:
+    """(B, n) -> (B, n): resampled sections concatenated (modulations.py:139-159)."""
+    _require_cuda(x, "mod_sig")
+    assert x.ndim == 2
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    ts = [_i32(v, x.device) for v in (sec_off, in_start, in_len, new_len, out_start)]
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().modfx_stretch_sections_f32(_ptr(x), _ptr(out), x.size(0), x.size(1),
+                                                         *[_ptr(t) for t in ts], _stream()))
+    return out

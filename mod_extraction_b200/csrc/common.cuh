@@ -116,6 +116,10 @@ __device__ __forceinline__ float upsample_ac(const float* __restrict__ lo, int I
     return __fmaf_rn(l0, lo[i0], __fmul_rn(l1, lo[i1]));
 }
 
+__device__ __forceinline__ float upsample_scale_ac_dev(int I, int O) {
+    return (O > 1) ? __fdiv_rn((float)(I - 1), (float)(O - 1)) : 0.0f;
+}
+
 inline float upsample_scale_ac(int64_t I, int64_t O) {
     return (O > 1) ? (float)(I - 1) / (float)(O - 1) : 0.0f;
 }

@@ -16,7 +16,8 @@ from . import _ops, util
 from ._lib import SHAPE_ID, SHAPES
 
 __all__ = ["SHAPES", "SHAPE_ID", "make_mod_signal", "make_mod_signal_batch", "make_rand_mod_signal",
-           "lfo_kernel_params"]
+           "lfo_kernel_params", "find_corners", "make_quasi_periodic", "make_quasi_periodic_batch",
+           "make_combined_mod_sig", "make_combined_mod_sig_batch"]
 
 
 def _device() -> tr.device:
@@ -124,3 +125,112 @@ def make_rand_mod_signal(batch_size: int,
         freqs.append(freq)
         shape_list.append(shape)
     return make_mod_signal_batch(n_samples, sr, freqs, phases, shape_list, None, device)
+
+
+# --------------------------------------------------------------------------- corners, quasi-periodic, combined
+
+def find_corners(mod_sig: T) -> Tuple[T, T]:
+    """modulations.py:219-238.  (B, n) -> (top, bottom), float tensors of 0/1 like the reference."""
+    assert mod_sig.ndim == 2
+    on_cpu = not mod_sig.is_cuda
+    m = mod_sig.detach().float().to(_device()) if on_cpu else mod_sig.detach().float()
+    top, bottom = _ops.find_corners(m)
+    top, bottom = top.to(mod_sig.dtype), bottom.to(mod_sig.dtype)
+    return (top.cpu(), bottom.cpu()) if on_cpu else (top, bottom)
+
+
+def _stretched_len(size: int, l_min: float, l_max: float, r_min: float, r_max: float, lr_split: float) -> int:
+    """Length decision of _time_stretch_section, modulations.py:104-116 (2 host RNG draws)."""
+    if util.sample_uniform(0.0, 1.0) < lr_split:
+        x = int((util.sample_uniform(l_min, l_max) * size) + 0.5)
+        return max(2, size - x)
+    x = int((util.sample_uniform(r_min, r_max) * size) + 0.5)
+    return size + x
+
+
+def make_quasi_periodic_batch(mod_sigs: T, l_min: float = 0.2, l_max: float = 0.2, r_min: float = 0.2,
+                              r_max: float = 0.2, lr_split: float = 0.5) -> T:
+    """make_quasi_periodic for a (B, n) batch: one corner kernel, one host pass that makes the
+    reference's RNG draws example by example in the reference's order, one resampling kernel.
+    Equivalent to calling the reference function on row 0, then row 1, ... under the same seed."""
+    assert mod_sigs.ndim == 2
+    dev = mod_sigs.device if mod_sigs.is_cuda else _device()
+    m = mod_sigs.detach().float().to(dev)
+    B, n = m.shape
+    top, bottom = _ops.find_corners(m)
+    top, bottom = top.cpu().numpy(), bottom.cpu().numpy()      # the one device->host sync
+    sec_off, in_start, in_len, new_len, out_start = [0], [], [], [], []
+    for b in range(B):
+        corners = top[b] if top[b].sum() > bottom[b].sum() else bottom[b]       # modulations.py:129-132
+        idxs = corners.nonzero()[0].tolist()
+        if len(idxs) >= 2:                                                       # modulations.py:136-137
+            prev, pos = 0, 0
+            for idx in idxs:                                                     # modulations.py:142-148
+                size = idx + 1 - prev
+                nl = _stretched_len(size, l_min, l_max, r_min, r_max, lr_split)
+                in_start.append(prev); in_len.append(size); new_len.append(nl); out_start.append(pos)
+                pos += nl - 1                                                    # new_section[:-1]
+                prev = idx
+            tail = n - prev                                                      # modulations.py:150-156
+            tail_new = tail + (n - (pos + tail)) if pos + tail < n else tail
+            in_start.append(prev); in_len.append(tail); new_len.append(tail_new); out_start.append(pos)
+        sec_off.append(len(in_start))
+    if not in_start:
+        return m.clone()
+    return _ops.stretch_sections(m, sec_off, in_start, in_len, new_len, out_start)
+
+
+def make_quasi_periodic(mod_sig: T,
+                        l_min: float = 0.2,
+                        l_max: float = 0.2,
+                        r_min: float = 0.2,
+                        r_max: float = 0.2,
+                        lr_split: float = 0.5) -> T:
+    """modulations.py:121-160."""
+    assert mod_sig.ndim == 1
+    on_cpu = not mod_sig.is_cuda
+    out = make_quasi_periodic_batch(mod_sig.unsqueeze(0), l_min, l_max, r_min, r_max, lr_split)[0]
+    return out.cpu() if on_cpu else out
+
+
+def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes: List[str], device=None) -> T:
+    """make_combined_mod_sig for B (freq, phase) pairs.  The number of RNG draws of an example
+    depends on the corners of the base shape it drew, so every candidate base shape is rendered and
+    corner-searched on the GPU first; the host then replays the reference's draw order exactly."""
+    device = _device() if device is None else device
+    f = tr.as_tensor(freqs, dtype=tr.float64).reshape(-1)
+    p = tr.as_tensor(phases, dtype=tr.float64).reshape(-1)
+    B, S = f.numel(), len(shapes)
+    sid = shape_ids(shapes)
+    cand = make_mod_signal_batch(n_samples, sr, f.repeat_interleave(S), p.repeat_interleave(S), sid.repeat(B),
+                                 None, device)                                   # (B*S, n)
+    _, bottom = _ops.find_corners(cand)
+    bottom = bottom.cpu().numpy().reshape(B, S, n_samples)
+    base = []
+    sec_off, sec_start, sec_len, sec_shape = [0], [], [], []
+    for b in range(B):
+        k = util.randint(0, S)                                                   # util.choice, modulations.py:196
+        base.append(b * S + k)
+        idxs = bottom[b, k].nonzero()[0].tolist()
+        if len(idxs) > 1:                                                        # modulations.py:203-209
+            for i, idx in enumerate(idxs[1:]):
+                prev = idxs[i]
+                section_len = idx - prev + 1
+                shape = shapes[util.randint(0, S)]
+                assert 0.0 < 1.0 < section_len / 2.0                             # make_mod_signal's assert :23
+                sec_start.append(prev); sec_len.append(section_len); sec_shape.append(SHAPE_ID[shape])
+        sec_off.append(len(sec_start))
+    out = cand[tr.tensor(base, device=device)].contiguous()
+    if sec_start:
+        _ops.lfo_sections_(out, sec_off, sec_start, sec_len, sec_shape)
+    return out
+
+
+def make_combined_mod_sig(n_samples: int,
+                          sr: float,
+                          freq: float,
+                          phase: float,
+                          shapes: List[str],
+                          device=None) -> T:
+    """modulations.py:191-210."""
+    return make_combined_mod_sig_batch(n_samples, sr, [float(freq)], [float(phase)], shapes, device)[0]
