@@ -148,6 +148,11 @@ int modfx_stretch_sections_f32(const float* in, float* out, int32_t B, int64_t n
  *   window    (n_fft,) device
  *   fb_start, fb_count (n_mels,) int32 device: first FFT bin and number of taps of each mel band
  *   fb_weight (n_mels, fb_stride) float32 device: tap weights, zero padded
+ *   x_row_stride / out_row_stride: distance in floats between consecutive rows of x / out (0 = dense:
+ *             T and n_mels*n_frames); row_index: optional (n_index,) int32 list of the rows to process
+ *             (NULL = all R).  Together they let dry and wet audio live in separate buffers while the
+ *             result lands in the (B, 2, n_mels, n_frames) tensor the extractor consumes, and let the
+ *             dry half start before the effects have finished.
  *   apply_log 1: out = log(max(mel, eps)) (models.py:207-208); 0: out = mel power, which is what
  *             the `spectrogram` attribute itself returns (SpecAugment sits between the two in
  *             training, models.py:201-205)
@@ -156,7 +161,8 @@ int modfx_stretch_sections_f32(const float* in, float* out, int32_t B, int64_t n
 int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T, int32_t n_fft, int32_t hop,
                      int32_t n_mels, const float* window, const int32_t* fb_start,
                      const int32_t* fb_count, const float* fb_weight, int32_t fb_stride, float eps,
-                     int32_t apply_log, void* stream);
+                     int32_t apply_log, int64_t x_row_stride, int64_t out_row_stride,
+                     const int32_t* row_index, int32_t n_index, void* stream);
 
 /*
  * Replaces PedalboardPhaserDataset.apply_pedalboard_phaser's DSP, mod_extraction/datasets.py:455-482

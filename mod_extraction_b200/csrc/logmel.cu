@@ -39,6 +39,8 @@ struct LogMelArgs {
     int fb_stride;
     float eps;
     int apply_log;
+    int64_t x_row_stride, out_row_stride;
+    const int32_t* row_index;
     int chunks;          // CTAs per row
     int iters_per_chunk; // iterations (of kFB frames) per CTA
 };
@@ -55,8 +57,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogMelArgs a)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int64_t row = blockIdx.x / a.chunks;
-    const int chunk = blockIdx.x - (int)row * a.chunks;
+    const int item = blockIdx.x / a.chunks;
+    const int chunk = blockIdx.x - item * a.chunks;
+    const int64_t row = a.row_index ? a.row_index[item] : item;
     const int T = (int)a.T;
     const int span = (kFB - 1) * a.hop + kNfft;      // samples staged per iteration
 
@@ -84,8 +87,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogMelArgs a)
         tw2s[i] = s;
     }
 
-    const float* xr = a.x + row * a.T;
-    float* orow = a.out + row * (int64_t)a.n_mels * a.n_frames;
+    const float* xr = a.x + row * a.x_row_stride;
+    float* orow = a.out + row * a.out_row_stride;
     const int it_begin = chunk * a.iters_per_chunk;
     const int it_end = min(it_begin + a.iters_per_chunk, (a.n_frames + kFB - 1) / kFB);
 
@@ -179,7 +182,8 @@ using namespace modfx;
 extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T, int32_t n_fft, int32_t hop,
                                 int32_t n_mels, const float* window, const int32_t* fb_start,
                                 const int32_t* fb_count, const float* fb_weight, int32_t fb_stride, float eps,
-                                int32_t apply_log, void* stream) {
+                                int32_t apply_log, int64_t x_row_stride, int64_t out_row_stride,
+                                const int32_t* row_index, int32_t n_index, void* stream) {
     MODFX_REQUIRE(x && out && window && fb_start && fb_count && fb_weight, "NULL pointer");
     MODFX_REQUIRE(R >= 0 && T >= 1, "bad shape R=%lld T=%lld", (long long)R, (long long)T);
     if (n_fft != kNfft) return fail(MODFX_ERR_UNSUPPORTED, "n_fft=%d (only 1024 is built)", n_fft);
@@ -188,12 +192,16 @@ extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T
     MODFX_REQUIRE(T > n_fft / 2, "reflect padding needs T > n_fft/2 (T=%lld)", (long long)T);   // torch raises too
     MODFX_REQUIRE(T < (1ll << 30), "T too long");
     MODFX_REQUIRE(n_mels >= 1 && fb_stride >= 1, "bad mel table");
-    if (R == 0) return MODFX_OK;
+    if (row_index) R = n_index;
+    if (R <= 0) return MODFX_OK;
     LogMelArgs a{};
     a.x = x; a.out = out; a.R = R; a.T = T; a.hop = hop; a.n_mels = n_mels;
     a.n_frames = (int)(T / hop) + 1;
     a.window = window; a.fb_start = fb_start; a.fb_count = fb_count; a.fb_weight = fb_weight;
     a.fb_stride = fb_stride; a.eps = eps; a.apply_log = apply_log;
+    a.x_row_stride = x_row_stride > 0 ? x_row_stride : T;
+    a.out_row_stride = out_row_stride > 0 ? out_row_stride : (int64_t)n_mels * a.n_frames;
+    a.row_index = row_index;
     const int iters = (a.n_frames + kFB - 1) / kFB;
     // enough CTAs to fill the chip twice over even for a handful of rows
     int chunks = 1;

@@ -102,6 +102,23 @@ class MelSpectrogram(nn.Module):
         return n_samples // self.hop_length + 1
 
     @torch.no_grad()
+    def forward_rows(self, x: Tensor, T: int, n_rows: int, out: Tensor, x_row_stride: int, out_row_stride: int,
+                     row_index: Optional[Tensor] = None) -> None:
+        """Strided / indexed variant used by the batch renderer: row r of the input starts at
+        ``x.data_ptr() + 4*r*x_row_stride`` and its (n_mels, n_frames) result is written at
+        ``out.data_ptr() + 4*r*out_row_stride``; ``row_index`` (int32, CUDA) selects rows."""
+        if self.fb_weight.device != x.device:
+            self.to(x.device)
+        vp = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().modfx_logmel_f32(
+                vp(x), vp(out), n_rows, T, self.n_fft, self.hop_length, self.n_mels, vp(self.window), vp(self.fb_start),
+                vp(self.fb_count), vp(self.fb_weight), self.fb_weight.size(1), float(self.eps),
+                1 if self.apply_log else 0, x_row_stride, out_row_stride, vp(row_index),
+                0 if row_index is None else row_index.numel(),
+                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    @torch.no_grad()
     def forward(self, x: Tensor, out: Optional[Tensor] = None) -> Tensor:
         if not x.is_cuda:
             raise RuntimeError("modfx: the log-mel front end needs a CUDA tensor (no CPU kernel)")
@@ -120,7 +137,8 @@ class MelSpectrogram(nn.Module):
             _lib.check(_lib.lib().modfx_logmel_f32(
                 vp(x), vp(out), R, T, self.n_fft, self.hop_length, self.n_mels, vp(self.window), vp(self.fb_start),
                 vp(self.fb_count), vp(self.fb_weight), self.fb_weight.size(1), float(self.eps),
-                1 if self.apply_log else 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                1 if self.apply_log else 0, 0, 0, None, 0,
+                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return out
 
 

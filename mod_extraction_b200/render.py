@@ -1,0 +1,139 @@
+"""Batch renderer for the ``train_lfo_interwoven_all`` data path (BASELINE config 4).
+
+Reference: ``InterwovenDataset.__getitem__`` picks ``datasets[idx % 3]`` -- flanger, chorus, phaser in
+the order of configs/data/interwoven_idmt_all.yml:12-17 (datasets.py:79-83); the flanger / chorus
+examples are rendered by ``MonoFlangerChorusModule`` from a control-rate LFO (data_modules.py:419-458),
+the phaser examples by pedalboard (datasets.py:455-482), and ``Spectral2DCNN.forward`` takes the log-mel
+of ``cat([dry, wet], dim=1)`` (lightning.py:106, models.py:199-208).
+
+Here one call renders the whole interleaved batch on the GPU: three effect launches on three streams
+(examples are selected through index lists, nothing is gathered or copied), and the log-mel kernel
+runs on a fourth stream -- the dry half at once, each wet group as soon as its effect has finished --
+writing straight into the (B, 2, n_mels, n_frames) tensor the extractor consumes.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _ops
+from ._ops import ModSource
+from .fx import _delay_samples
+from .models import LogMelSpectrogram
+
+FLANGER, CHORUS, PHASER = 0, 1, 2       # order of configs/data/interwoven_idmt_all.yml
+
+
+class InterwovenRenderer:
+    def __init__(self, n_samples: int = 88200, sr: float = 44100.0, device=None,
+                 flanger_delays_ms: Tuple[float, float] = (1.0, 10.0),      # configs/data/gen_idmt_fl.yml
+                 chorus_delays_ms: Tuple[float, float] = (30.0, 10.0),      # configs/data/gen_idmt_ch.yml
+                 n_mels: int = 256, n_fft: int = 1024, hop_len: int = 256, eps: float = 1e-7,
+                 phaser_buffer_size: int = 8192, concurrent: bool = True) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("mod_extraction_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_samples, self.sr = n_samples, sr
+        self.fl = tuple(_delay_samples(ms, sr) for ms in flanger_delays_ms)
+        self.ch = tuple(_delay_samples(ms, sr) for ms in chorus_delays_ms)
+        self.front = LogMelSpectrogram(int(sr), n_fft, hop_len, n_mels, eps=eps).to(self.device)
+        self.n_frames = self.front.n_frames(n_samples)
+        self.phaser_buffer_size = phaser_buffer_size
+        self.concurrent = concurrent
+        self._streams = [torch.cuda.Stream(device=self.device) for _ in range(4)] if concurrent else None
+        self._idx_cache: Dict[int, Tuple[Tensor, ...]] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _groups(self, effect: Tensor):
+        key = id(effect)
+        hit = self._idx_cache.get(key)
+        if hit is not None and hit[0] is effect:
+            return hit[1:]
+        e = effect.detach().cpu()
+        groups = []
+        for k in (FLANGER, CHORUS, PHASER):
+            idx = torch.nonzero(e == k).reshape(-1).to(torch.int32)
+            groups.append(idx.to(self.device))
+        B = e.numel()
+        dry_rows = torch.arange(B, dtype=torch.int32, device=self.device)
+        self._idx_cache = {key: (effect, *groups, dry_rows)}
+        return (*groups, dry_rows)
+
+    def alloc_outputs(self, B: int) -> Tuple[Tensor, Tensor]:
+        wet = torch.empty((B, 1, self.n_samples), device=self.device, dtype=torch.float32)
+        logmel = torch.empty((B, 2, self.front.n_mels, self.n_frames), device=self.device, dtype=torch.float32)
+        return wet, logmel
+
+    # ------------------------------------------------------------------ the hot path
+    @torch.no_grad()
+    def render(self, dry: Tensor, effect: Tensor, mod_lo: Tensor, fc: Dict[str, Tensor], ph: Dict[str, Tensor],
+               wet: Optional[Tensor] = None, logmel: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """dry (B,1,N) CUDA float32; effect (B,) ints in {0: flanger, 1: chorus, 2: phaser};
+        mod_lo (B, n_lo) control-rate LFO of the flanger / chorus examples (rows of phaser examples are
+        ignored); fc: feedback, min_delay_width, width, depth, mix as (B,) tensors (data_modules.py:421-445);
+        ph: rate_hz, depth, centre_frequency_hz, feedback, mix as (B,) tensors (datasets.py:461-470).
+        Returns (wet (B,1,N), logmel (B,2,n_mels,n_frames))."""
+        assert dry.is_cuda and dry.dtype == torch.float32 and dry.ndim == 3 and dry.size(1) == 1
+        dry = dry.contiguous()
+        B, _, N = dry.shape
+        assert N == self.n_samples
+        if wet is None or logmel is None:
+            w2, l2 = self.alloc_outputs(B)
+            wet = w2 if wet is None else wet
+            logmel = l2 if logmel is None else logmel
+        i_fl, i_ch, i_ph, _ = self._groups(effect)
+        fc_args = [fc[k] for k in ("feedback", "min_delay_width", "width", "depth", "mix")]
+        ph_args = [ph[k] for k in ("rate_hz", "depth", "centre_frequency_hz", "feedback", "mix")]
+        src = ModSource.control_rate(mod_lo)
+        nm = self.front.n_mels * self.n_frames
+        dry2, wet2 = dry.view(B, N), wet.view(B, N)
+        lm_dry, lm_wet = logmel.view(-1), logmel.view(-1)[nm:]
+
+        def effects_fl():
+            _ops.flanger_chorus(dry, src, self.fl[0], self.fl[1], *fc_args, example_index=i_fl, out=wet)
+
+        def effects_ch():
+            _ops.flanger_chorus(dry, src, self.ch[0], self.ch[1], *fc_args, example_index=i_ch, out=wet)
+
+        def effects_ph():
+            _ops.phaser(dry2, self.sr, *ph_args, block=self.phaser_buffer_size, example_index=i_ph, out=wet2)
+
+        def mel(x2, out_flat, rows):
+            if rows is not None and rows.numel() == 0:
+                return
+            self.front.forward_rows(x2, N, B, out_flat, N, 2 * nm, rows)
+
+        if not self.concurrent:
+            effects_fl(); effects_ch(); effects_ph()
+            mel(dry2, lm_dry, None)
+            mel(wet2, lm_wet, None)
+            return wet, logmel
+
+        cur = torch.cuda.current_stream(self.device)
+        s_fl, s_ch, s_ph, s_lm = self._streams
+        start = torch.cuda.Event()
+        start.record(cur)
+        done = []
+        for s, fn in ((s_fl, effects_fl), (s_ch, effects_ch), (s_ph, effects_ph)):
+            s.wait_event(start)
+            with torch.cuda.stream(s):
+                fn()
+                ev = torch.cuda.Event()
+                ev.record(s)
+                done.append(ev)
+        s_lm.wait_event(start)
+        with torch.cuda.stream(s_lm):
+            mel(dry2, lm_dry, None)                       # needs no effect: starts immediately
+            for ev, rows in ((done[1], i_ch), (done[2], i_ph), (done[0], i_fl)):   # flanger has the longest tail
+                s_lm.wait_event(ev)
+                mel(wet2, lm_wet, rows)
+            fin = torch.cuda.Event()
+            fin.record(s_lm)
+        cur.wait_event(fin)
+        for t in (dry, mod_lo, wet, logmel, *fc_args, *ph_args):
+            if isinstance(t, Tensor) and t.is_cuda:
+                for s in self._streams:
+                    t.record_stream(s)
+        return wet, logmel
