@@ -148,6 +148,7 @@ int modfx_stretch_sections_f32(const float* in, float* out, int32_t B, int64_t n
  *   window    (n_fft,) device
  *   fb_start, fb_count (n_mels,) int32 device: first FFT bin and number of taps of each mel band
  *   fb_weight (n_mels, fb_stride) float32 device: tap weights, zero padded
+ *   fb_taps   sum of fb_count (the kernel keeps a compact copy of the table in shared memory)
  *   x_row_stride / out_row_stride: distance in floats between consecutive rows of x / out (0 = dense:
  *             T and n_mels*n_frames); row_index: optional (n_index,) int32 list of the rows to process
  *             (NULL = all R).  Together they let dry and wet audio live in separate buffers while the
@@ -160,8 +161,8 @@ int modfx_stretch_sections_f32(const float* in, float* out, int32_t B, int64_t n
  */
 int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T, int32_t n_fft, int32_t hop,
                      int32_t n_mels, const float* window, const int32_t* fb_start,
-                     const int32_t* fb_count, const float* fb_weight, int32_t fb_stride, float eps,
-                     int32_t apply_log, int64_t x_row_stride, int64_t out_row_stride,
+                     const int32_t* fb_count, const float* fb_weight, int32_t fb_stride, int32_t fb_taps,
+                     float eps, int32_t apply_log, int64_t x_row_stride, int64_t out_row_stride,
                      const int32_t* row_index, int32_t n_index, void* stream);
 
 /*

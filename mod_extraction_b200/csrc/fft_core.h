@@ -26,6 +26,10 @@ namespace modfx {
                    1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f, \
                    0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f}
 
+// cos/sin(2 pi j / 64), j = 0..31
+#define MODFX_C64 {1.0f, 0.99518472667219693f, 0.98078528040323043f, 0.95694033573220882f, 0.92387953251128674f, 0.88192126434835505f, 0.83146961230254524f, 0.77301045336273699f, 0.70710678118654757f, 0.63439328416364549f, 0.55557023301960229f, 0.47139673682599781f, 0.38268343236508984f, 0.29028467725446233f, 0.19509032201612833f, 0.09801714032956077f, 0.0f, -0.098017140329560645f, -0.19509032201612819f, -0.29028467725446216f, -0.38268343236508973f, -0.4713967368259977f, -0.55557023301960196f, -0.63439328416364538f, -0.70710678118654746f, -0.77301045336273699f, -0.83146961230254535f, -0.88192126434835494f, -0.92387953251128674f, -0.95694033573220882f, -0.98078528040323043f, -0.99518472667219682f}
+#define MODFX_S64 {0.0f, 0.098017140329560604f, 0.19509032201612825f, 0.29028467725446233f, 0.38268343236508978f, 0.47139673682599764f, 0.55557023301960218f, 0.63439328416364549f, 0.70710678118654746f, 0.77301045336273699f, 0.83146961230254524f, 0.88192126434835494f, 0.92387953251128674f, 0.95694033573220894f, 0.98078528040323043f, 0.99518472667219682f, 1.0f, 0.99518472667219693f, 0.98078528040323043f, 0.95694033573220894f, 0.92387953251128674f, 0.88192126434835505f, 0.83146961230254546f, 0.7730104533627371f, 0.70710678118654757f, 0.63439328416364549f, 0.55557023301960218f, 0.47139673682599786f, 0.38268343236508989f, 0.29028467725446239f, 0.19509032201612861f, 0.098017140329560826f}
+
 template <int N>
 struct BitRev;
 template <>

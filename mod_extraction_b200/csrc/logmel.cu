@@ -24,7 +24,7 @@ constexpr int kBins = kNfft / 2 + 1;     // 513
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * kWarp;
 constexpr int kFB = 2 * kWarps;          // frames per CTA iteration
-constexpr int kPStride = kFB + 1;        // padded row of the power matrix P[bin][frame]
+constexpr int kPStride = kFB;            // row of the power matrix P[bin][frame]: 8 floats = two float4
 constexpr int kEStride = 33;             // padded row of the pass-1 -> pass-2 exchange buffer
 
 struct LogMelArgs {
@@ -37,6 +37,7 @@ struct LogMelArgs {
     const int32_t* fb_count;
     const float* fb_weight;
     int fb_stride;
+    int fb_taps;         // capacity of the compact in-smem weight table (>= sum of fb_count)
     float eps;
     int apply_log;
     int64_t x_row_stride, out_row_stride;
@@ -52,7 +53,11 @@ __device__ __forceinline__ int reflect_index(int i, int T) {
     return max(0, min(i, T - 1));      // frames past the end of a short clip are computed but never stored
 }
 
-__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogMelArgs a) {
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+}
+
+__global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -66,14 +71,14 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogMelArgs a)
     float* win = smem;                         // [1024]
     float* tw1c = win + kNfft;                 // [16][32]  cos(-2 pi n2 k1 / 512)
     float* tw1s = tw1c + 512;
-    float* tw2c = tw1s + 512;                  // [512]     cos(2 pi k / 1024)
-    float* tw2s = tw2c + 512;
-    float* P = tw2s + 512;                     // [513][kPStride]
-    float* E = P + kBins * kPStride + 3;       // per warp: Er[32][33], Ei[32][33]
-    E = E - ((E - smem) & 3);                  // keep 16-byte alignment
+    float* P = tw1s + 512;                     // [513][8]
+    float* E = P + kBins * kPStride + 4;       // per warp: Er[32][33], Ei[32][33]  (kBins*8 + 4 keeps 16 B alignment)
     float* Er = E + warp * (2 * 32 * kEStride);
     float* Ei = Er + 32 * kEStride;
-    float* sbuf = E + kWarps * (2 * 32 * kEStride);   // [span]
+    float* sbuf = E + kWarps * (2 * 32 * kEStride);             // [span rounded up to 4]
+    float* melw = sbuf + ((span + 3) & ~3);                     // [fb_taps] band weights, bands back to back
+    unsigned short* moff = reinterpret_cast<unsigned short*>(melw + a.fb_taps);    // [n_mels + 1] first weight of band m
+    unsigned short* mstart = moff + a.n_mels + 2;                                  // [n_mels] first FFT bin of band m
 
     for (int i = tid; i < kNfft; i += kThreads) win[i] = a.window[i];
     for (int i = tid; i < 512; i += kThreads) {
@@ -82,49 +87,81 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogMelArgs a)
         sincospif(-(float)(n2 * k1) / 256.0f, &s, &c);
         tw1c[i] = c;
         tw1s[i] = s;
-        sincospif((float)i / 512.0f, &s, &c);
-        tw2c[i] = c;
-        tw2s[i] = s;
     }
+    // compact copy of the banded mel table (<= 14 taps per band for the reference configuration)
+    if (tid == 0) {
+        int off = 0;
+        for (int m = 0; m < a.n_mels; ++m) {
+            moff[m] = (unsigned short)off;
+            off += min(a.fb_count[m], a.fb_taps - off);
+        }
+        moff[a.n_mels] = (unsigned short)off;
+    }
+    __syncthreads();
+    for (int m = tid; m < a.n_mels; m += kThreads) {
+        mstart[m] = (unsigned short)a.fb_start[m];
+        const int o = moff[m], c = moff[m + 1] - o;
+        for (int j = 0; j < c; ++j) melw[o + j] = a.fb_weight[(int64_t)m * a.fb_stride + j];
+    }
+    // split twiddle of this lane's bins k = k1 + 16 k2: w_k = w_{k1} * w_{16 k2}
+    float c1, s1;
+    sincospif((float)(lane & 15) / 512.0f, &s1, &c1);
 
     const float* xr = a.x + row * a.x_row_stride;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(xr) & 15) == 0) && ((a.hop & 3) == 0);
     float* orow = a.out + row * a.out_row_stride;
     const int it_begin = chunk * a.iters_per_chunk;
     const int it_end = min(it_begin + a.iters_per_chunk, (a.n_frames + kFB - 1) / kFB);
+    bool prefetched = false;
 
     for (int it = it_begin; it < it_end; ++it) {
         const int t0 = it * kFB;
         // ---- stage the audio span of frames t0 .. t0+7 (center=True: frame t starts at t*hop - 512)
         const int s0 = t0 * a.hop - kNfft / 2;
-        for (int i = tid; i < span; i += kThreads) sbuf[i] = xr[reflect_index(s0 + i, T)];
+        if (prefetched) {
+            asm volatile("cp.async.wait_group 0;\n" ::);
+        } else {
+            for (int i = tid; i < span; i += kThreads) sbuf[i] = xr[reflect_index(s0 + i, T)];
+        }
         __syncthreads();
 
         const int lf = 2 * warp;                        // local index of this warp's first frame
-        if (t0 + lf < a.n_frames) {
+        const bool active = t0 + lf < a.n_frames;
+        float re[32], im[32];
+        if (active) {
             // ---- pass 1: lane = n2; 16-point FFT over n1 of z[32 n1 + n2], both frames
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
-                float re[16], im[16];
+                float r16[16], i16[16];
                 const float* fr = sbuf + (lf + f) * a.hop;
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) {
                     const float2 v = *reinterpret_cast<const float2*>(fr + 64 * n1 + 2 * lane);
                     const float2 w = *reinterpret_cast<const float2*>(win + 64 * n1 + 2 * lane);
-                    re[n1] = v.x * w.x;
-                    im[n1] = v.y * w.y;
+                    r16[n1] = v.x * w.x;
+                    i16[n1] = v.y * w.y;
                 }
-                fft_dif<16>(re, im);
+                fft_dif<16>(r16, i16);
 #pragma unroll
                 for (int k1 = 0; k1 < 16; ++k1) {
-                    const float yr = re[BitRev<16>::of(k1)], yi = im[BitRev<16>::of(k1)];
+                    const float yr = r16[BitRev<16>::of(k1)], yi = i16[BitRev<16>::of(k1)];
                     const float c = tw1c[k1 * 32 + lane], s = tw1s[k1 * 32 + lane];
                     Er[(f * 16 + k1) * kEStride + lane] = yr * c - yi * s;
                     Ei[(f * 16 + k1) * kEStride + lane] = yr * s + yi * c;
                 }
             }
-            __syncwarp();
+        }
+        __syncthreads();        // every warp is done with sbuf: the next span may land in it
+        {
+            const int s1n = (t0 + kFB) * a.hop - kNfft / 2;
+            prefetched = (it + 1 < it_end) && vec_ok && s1n >= 0 && (s1n + span <= T);
+            if (prefetched) {
+                for (int i = tid; i < (span >> 2); i += kThreads) cp_async16(sbuf + 4 * i, xr + s1n + 4 * i);
+                asm volatile("cp.async.commit_group;\n" ::);
+            }
+        }
+        if (active) {
             // ---- pass 2: lane = (frame f, k1); 32-point FFT over n2
-            float re[32], im[32];
 #pragma unroll
             for (int n2 = 0; n2 < 32; ++n2) {
                 re[n2] = Er[lane * kEStride + n2];
@@ -132,6 +169,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogMelArgs a)
             }
             fft_dif<32>(re, im);
             // ---- real-FFT split + power: this lane owns bins k = k1 + 16 k2 of its frame
+            constexpr float C64[32] = MODFX_C64;
+            constexpr float S64[32] = MODFX_S64;
             const int f = lane >> 4, k1 = lane & 15;
             const int partner = (lane & 16) | ((16 - k1) & 15);
             float* Pcol = P + (lf + f);
@@ -146,8 +185,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogMelArgs a)
                     pr = re[src_self];
                     pi = im[src_self];
                 }
-                const int k = k1 + 16 * k2;
-                Pcol[k * kPStride] = rfft_split_power(re[own], im[own], pr, pi, tw2c[k], tw2s[k]);
+                const float c = c1 * C64[k2] - s1 * S64[k2];            // cos(2 pi k / 1024)
+                const float s = s1 * C64[k2] + c1 * S64[k2];
+                Pcol[(k1 + 16 * k2) * kPStride] = rfft_split_power(re[own], im[own], pr, pi, c, s);
             }
             if (k1 == 0) {
                 const float v = re[0] - im[0];          // X[512] = Re Z[0] - Im Z[0]
@@ -156,21 +196,40 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogMelArgs a)
         }
         __syncthreads();
 
-        // ---- banded mel projection + clip + log; thread = (frame t, mel group)
+        // ---- banded mel projection + clip + log.  A thread owns whole mel bands (a low one and its
+        // mirror from the top, so the 1..14 taps balance) and all 8 frames of the iteration: per tap
+        // one weight, two 16-byte reads of the power row, eight FMAs.
         {
-            const int t = tid & (kFB - 1);
-            const int mg = tid / kFB;                   // 0 .. kThreads/kFB - 1
-            const bool live = (t0 + t) < a.n_frames;
-            for (int m = mg; m < a.n_mels; m += kThreads / kFB) {
-                const int start = __ldg(a.fb_start + m);
-                const int cnt = __ldg(a.fb_count + m);
-                const float* w = a.fb_weight + (int64_t)m * a.fb_stride;
-                float acc = 0.0f;
-                for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(w + j), P[(start + j) * kPStride + t], acc);
-                if (live) orow[(int64_t)m * a.n_frames + t0 + t] = a.apply_log ? logf(fmaxf(acc, a.eps)) : acc;
+            const int half = (a.n_mels + 1) / 2;
+            for (int mm = tid; mm < half; mm += kThreads) {
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    const int m = side ? (a.n_mels - 1 - mm) : mm;
+                    if (side && m <= mm) break;
+                    const int o = moff[m], cnt = moff[m + 1] - o;
+                    const float* w = melw + o;
+                    float acc[kFB];
+#pragma unroll
+                    for (int t = 0; t < kFB; ++t) acc[t] = 0.0f;
+                    const float4* prow = reinterpret_cast<const float4*>(P + (int)mstart[m] * kPStride);
+                    for (int j = 0; j < cnt; ++j) {
+                        const float wj = w[j];
+                        const float4 p0 = prow[2 * j], p1 = prow[2 * j + 1];
+                        acc[0] = fmaf(wj, p0.x, acc[0]); acc[1] = fmaf(wj, p0.y, acc[1]);
+                        acc[2] = fmaf(wj, p0.z, acc[2]); acc[3] = fmaf(wj, p0.w, acc[3]);
+                        acc[4] = fmaf(wj, p1.x, acc[4]); acc[5] = fmaf(wj, p1.y, acc[5]);
+                        acc[6] = fmaf(wj, p1.z, acc[6]); acc[7] = fmaf(wj, p1.w, acc[7]);
+                    }
+                    float* op = orow + (int64_t)m * a.n_frames + t0;
+                    const int live = min(kFB, a.n_frames - t0);
+#pragma unroll
+                    for (int t = 0; t < kFB; ++t)
+                        if (t < live) op[t] = a.apply_log ? __logf(fmaxf(acc[t], a.eps)) : acc[t];
+                }
             }
         }
-        __syncthreads();
+        // no barrier here: the next iteration's first barrier orders this read of P before the next write
+        // (P is only written after the barrier that follows pass 1)
     }
 }
 
@@ -181,8 +240,8 @@ using namespace modfx;
 
 extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T, int32_t n_fft, int32_t hop,
                                 int32_t n_mels, const float* window, const int32_t* fb_start,
-                                const int32_t* fb_count, const float* fb_weight, int32_t fb_stride, float eps,
-                                int32_t apply_log, int64_t x_row_stride, int64_t out_row_stride,
+                                const int32_t* fb_count, const float* fb_weight, int32_t fb_stride, int32_t fb_taps,
+                                float eps, int32_t apply_log, int64_t x_row_stride, int64_t out_row_stride,
                                 const int32_t* row_index, int32_t n_index, void* stream) {
     MODFX_REQUIRE(x && out && window && fb_start && fb_count && fb_weight, "NULL pointer");
     MODFX_REQUIRE(R >= 0 && T >= 1, "bad shape R=%lld T=%lld", (long long)R, (long long)T);
@@ -191,7 +250,9 @@ extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T
         return fail(MODFX_ERR_UNSUPPORTED, "hop=%d (even hops in [2, 512] are built)", hop);
     MODFX_REQUIRE(T > n_fft / 2, "reflect padding needs T > n_fft/2 (T=%lld)", (long long)T);   // torch raises too
     MODFX_REQUIRE(T < (1ll << 30), "T too long");
-    MODFX_REQUIRE(n_mels >= 1 && fb_stride >= 1, "bad mel table");
+    MODFX_REQUIRE(n_mels >= 1 && fb_stride >= 1 && fb_taps >= 1, "bad mel table");
+    if (n_mels > 4096 || fb_taps > 8192 || (int64_t)n_mels * 0 + fb_taps > 65535)
+        return fail(MODFX_ERR_UNSUPPORTED, "mel table too large for shared memory (n_mels=%d taps=%d)", n_mels, fb_taps);
     if (row_index) R = n_index;
     if (R <= 0) return MODFX_OK;
     LogMelArgs a{};
@@ -199,6 +260,7 @@ extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T
     a.n_frames = (int)(T / hop) + 1;
     a.window = window; a.fb_start = fb_start; a.fb_count = fb_count; a.fb_weight = fb_weight;
     a.fb_stride = fb_stride; a.eps = eps; a.apply_log = apply_log;
+    a.fb_taps = fb_taps;
     a.x_row_stride = x_row_stride > 0 ? x_row_stride : T;
     a.out_row_stride = out_row_stride > 0 ? out_row_stride : (int64_t)n_mels * a.n_frames;
     a.row_index = row_index;
@@ -212,8 +274,9 @@ extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T
     a.chunks = (iters + a.iters_per_chunk - 1) / a.iters_per_chunk;
     MODFX_REQUIRE(R * a.chunks < (1ll << 31), "grid too large");
     const int span = (kFB - 1) * hop + kNfft;
-    const size_t smem = sizeof(float) * (size_t)(kNfft + 4 * 512 + kBins * kPStride + 8 +
-                                                 kWarps * 2 * 32 * kEStride + span);
+    const size_t smem = sizeof(float) * (size_t)(kNfft + 2 * 512 + kBins * kPStride + 4 + kWarps * 2 * 32 * kEStride +
+                                                 ((span + 3) & ~3) + fb_taps) +
+                        sizeof(unsigned short) * (size_t)(2 * n_mels + 4) + 16;
     MODFX_CUDA_OK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     logmel_kernel<<<(unsigned)(R * a.chunks), kThreads, smem, as_stream(stream)>>>(a);
     MODFX_CUDA_OK(cudaGetLastError());

@@ -85,6 +85,7 @@ class MelSpectrogram(nn.Module):
         assert fb.shape == (n_fft // 2 + 1, n_mels)
         window = torch.hann_window(n_fft, periodic=True) if window is None else window.detach().float().cpu()
         start, count, weight = banded(fb)
+        self.fb_taps = max(1, int(count.sum()))
         self.register_buffer("fb", fb, persistent=False)
         self.register_buffer("window", window, persistent=False)
         self.register_buffer("fb_start", start, persistent=False)
@@ -113,7 +114,7 @@ class MelSpectrogram(nn.Module):
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().modfx_logmel_f32(
                 vp(x), vp(out), n_rows, T, self.n_fft, self.hop_length, self.n_mels, vp(self.window), vp(self.fb_start),
-                vp(self.fb_count), vp(self.fb_weight), self.fb_weight.size(1), float(self.eps),
+                vp(self.fb_count), vp(self.fb_weight), self.fb_weight.size(1), self.fb_taps, float(self.eps),
                 1 if self.apply_log else 0, x_row_stride, out_row_stride, vp(row_index),
                 0 if row_index is None else row_index.numel(),
                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
@@ -136,7 +137,7 @@ class MelSpectrogram(nn.Module):
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().modfx_logmel_f32(
                 vp(x), vp(out), R, T, self.n_fft, self.hop_length, self.n_mels, vp(self.window), vp(self.fb_start),
-                vp(self.fb_count), vp(self.fb_weight), self.fb_weight.size(1), float(self.eps),
+                vp(self.fb_count), vp(self.fb_weight), self.fb_weight.size(1), self.fb_taps, float(self.eps),
                 1 if self.apply_log else 0, 0, 0, None, 0,
                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return out

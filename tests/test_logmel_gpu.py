@@ -58,7 +58,7 @@ def test_mel_power_matches_attribute_semantics():
     l = _front(log=True, fb=g["fb"], window=g["window"])(x)
     assert p.shape == (2, 2, 256, 12345 // 256 + 1)
     assert float(p.min()) >= 0.0
-    assert torch.equal(torch.log(torch.clip(p, min=1e-7)), l)
+    assert float((torch.log(torch.clip(p, min=1e-7)) - l).abs().max()) <= 1e-5     # fast log: <= 3 ulp
 
 
 @pytest.mark.parametrize("T", [513, 1024, 2047, 2048, 2049, 88200, 100000])
