@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
             constexpr float S64[32] = MODFX_S64;
             const int f = lane >> 4, k1 = lane & 15;
             const int partner = (lane & 16) | ((16 - k1) & 15);
-            float* Pcol = P + (lf + f);
+            // the two 16-byte halves of a power row are swapped on every other group of 4 rows so that
+            // rows r and r+4 (same banks) are read / written through different banks
+            float* Pcol = P + ((lf + f) ^ (((k1 >> 2) & 1) << 2));
 #pragma unroll
             for (int k2 = 0; k2 < 32; ++k2) {
                 const int own = BitRev<32>::of(k2);
@@ -211,10 +213,13 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
                     float acc[kFB];
 #pragma unroll
                     for (int t = 0; t < kFB; ++t) acc[t] = 0.0f;
-                    const float4* prow = reinterpret_cast<const float4*>(P + (int)mstart[m] * kPStride);
+                    const int r0 = (int)mstart[m];
                     for (int j = 0; j < cnt; ++j) {
                         const float wj = w[j];
-                        const float4 p0 = prow[2 * j], p1 = prow[2 * j + 1];
+                        const int r = r0 + j;
+                        const int sw = (r >> 2) & 1;
+                        const float4 p0 = *reinterpret_cast<const float4*>(P + r * kPStride + 4 * sw);
+                        const float4 p1 = *reinterpret_cast<const float4*>(P + r * kPStride + 4 - 4 * sw);
                         acc[0] = fmaf(wj, p0.x, acc[0]); acc[1] = fmaf(wj, p0.y, acc[1]);
                         acc[2] = fmaf(wj, p0.z, acc[2]); acc[3] = fmaf(wj, p0.w, acc[3]);
                         acc[4] = fmaf(wj, p1.x, acc[4]); acc[5] = fmaf(wj, p1.y, acc[5]);
