@@ -7,7 +7,7 @@
 // strictly serial per example: ~100 dependent cycles per sample.  It is parallelised over time with
 // a chunked affine scan (DESIGN.md "P1"):
 //   K0  control-rate cutoff: the oscillator phase is accumulated in float32 exactly like the
-//       reference (sequentially inside each 8192-sample host block), then mapped to the all-pass
+//       reference (sequentially inside each 8192-sample host block) and mapped to the all-pass
 //       coefficient c = 2G-1 for every 4th sample;
 //   K1  for every chunk of 128 samples, 8 independent runs give the chunk's state-transition matrix
 //       (7 homogeneous runs from the unit states) and its zero-state response (1 run with the audio);
@@ -45,72 +45,115 @@ struct PhaserArgs {
 
 __device__ __forceinline__ int example_of(const PhaserArgs& a, int item) { return a.index ? a.index[item] : item; }
 
-// ---- K0a: oscillator phase per control point (juce::dsp::Oscillator semantics) ------------
-// One thread per (example, host block).  Inside a block the phase advances by `inc` per control
-// point with a wrap at 2 pi; between blocks it advances by inc * (points in the block) in one step.
-__global__ void phaser_phase_kernel(const PhaserArgs a, int n_blocks) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= a.n_items * n_blocks) return;
-    const int item = gid / n_blocks, blk = gid - item * n_blocks;
-    const int b = example_of(a, item);
+// ---- K0: control-rate all-pass coefficient ----------------------------------------------------
+// juce::dsp::Oscillator semantics: inside a host block the phase advances by `inc` per control point
+// with a wrap at 2 pi (sequential float32 adds, reproduced exactly); between blocks it advances by
+// inc * (points in the block) in one step.  A CTA owns 32 (example, host block) pairs: warp 0 walks
+// the 32 phase sequences (lane = pair) 32 control points at a time into a shared tile, then all 256
+// threads map the 1024 phases to c = 2G-1 (sin, 10^x, tan: the expensive part) and store them with
+// 128-byte rows.
+constexpr int kK0Threads = 256;
+__global__ void __launch_bounds__(kK0Threads) phaser_ctl_kernel(const PhaserArgs a, int n_blocks) {
+    __shared__ float tile[32][33];
+    __shared__ int j0s[32], j1s[32], items[32];
+    __shared__ float vol[32], ctr[32];
+    const int tid = threadIdx.x;
     const float two_pi = MODFX_TWO_PI_F;
-    const float sr_down = (float)((double)a.sr / (double)kUpd);
-    const float inc = a.rate[b] * (two_pi / sr_down);
-    float phase = 0.0f;
-    for (int i = 0; i < blk; ++i) {
-        const int64_t s0 = (int64_t)i * a.block, s1 = min((int64_t)(i + 1) * a.block, (int64_t)a.N);
-        const int n_down = (int)((s1 + kUpd - 1) / kUpd - (s0 + kUpd - 1) / kUpd);
-        float next = phase + inc * (float)n_down;
-        while (next >= two_pi) next -= two_pi;
-        phase = next;
-    }
-    const int64_t s0 = (int64_t)blk * a.block, s1 = min((int64_t)(blk + 1) * a.block, (int64_t)a.N);
-    const int j0 = (int)((s0 + kUpd - 1) / kUpd), j1 = (int)((s1 + kUpd - 1) / kUpd);
-    float* out = a.C + (int64_t)item * a.n_ctl;
-    float p = phase;
-    for (int j = j0; j < j1; ++j) {
-        out[j] = p;
-        float next = p + inc;
-        while (next >= two_pi) next -= two_pi;
-        p = next;
-    }
-}
-
-// ---- K0b: phase -> all-pass coefficient c = 2G - 1 ---------------------------------------------
-__global__ void phaser_coef_kernel(const PhaserArgs a) {
-    const int item = blockIdx.y;
-    const int b = example_of(a, item);
     const float f_lo = 20.0f;
     const double f_hi_d = (0.49 * (double)a.sr < 20000.0) ? 0.49 * (double)a.sr : 20000.0;
     const float log_min = log10f(f_lo), log_max = log10f((float)f_hi_d);
-    const float norm_centre = (log10f(a.centre[b]) - log_min) / (log_max - log_min);   // mapFromLog10
-    const float osc_vol = a.depth[b] * 0.5f;
-    float* c = a.C + (int64_t)item * a.n_ctl;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_ctl; j += gridDim.x * blockDim.x) {
-        float lfo = sinf(c[j] - MODFX_PI_F) * osc_vol + norm_centre;
-        lfo = fminf(fmaxf(lfo, 0.0f), 1.0f);
-        const float fc = powf(10.0f, lfo * (log_max - log_min) + log_min);               // mapToLog10
-        const float g = (float)tan(3.14159265358979323846 * (double)fc / (double)a.sr);  // TPT prewarp
-        const float G = g / (1.0f + g);
-        c[j] = 2.0f * G - 1.0f;
+    const float log_span = log_max - log_min;
+    const float w0 = MODFX_PI_F / a.sr;
+    float p = 0.0f, inc = 0.0f;
+    if (tid < 32) {
+        const int pair = blockIdx.x * 32 + tid;
+        const bool live = pair < a.n_items * n_blocks;
+        const int item = live ? pair / n_blocks : 0, blk = live ? pair - item * n_blocks : 0;
+        const int b = example_of(a, item);
+        const float sr_down = (float)((double)a.sr / (double)kUpd);
+        inc = a.rate[b] * (two_pi / sr_down);
+        for (int i = 0; i < blk; ++i) {
+            const int64_t s0 = (int64_t)i * a.block, s1 = min((int64_t)(i + 1) * a.block, (int64_t)a.N);
+            const int n_down = (int)((s1 + kUpd - 1) / kUpd - (s0 + kUpd - 1) / kUpd);
+            float next = p + inc * (float)n_down;
+            while (next >= two_pi) next -= two_pi;
+            p = next;
+        }
+        const int64_t s0 = (int64_t)blk * a.block, s1 = min((int64_t)(blk + 1) * a.block, (int64_t)a.N);
+        j0s[tid] = live ? (int)((s0 + kUpd - 1) / kUpd) : 0;
+        j1s[tid] = live ? (int)((s1 + kUpd - 1) / kUpd) : 0;
+        items[tid] = item;
+        vol[tid] = a.depth[b] * 0.5f;                                           // oscVolume target
+        ctr[tid] = (log10f(a.centre[b]) - log_min) / log_span;                   // mapFromLog10(centre)
+    }
+    const int rounds = (int)((((int64_t)a.block + kUpd - 1) / kUpd + 31) / 32) + 1;
+    for (int r = 0; r < rounds; ++r) {
+        __syncthreads();
+        if (tid < 32) {
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) {
+                tile[tid][q] = p;
+                float next = p + inc;
+                while (next >= two_pi) next -= two_pi;
+                p = next;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < 32 * 32; e += kK0Threads) {
+            const int t = e >> 5, q = e & 31;
+            const int j = j0s[t] + 32 * r + q;
+            if (j < j1s[t]) {
+                float lfo = sinf(tile[t][q] - MODFX_PI_F) * vol[t] + ctr[t];
+                lfo = fminf(fmaxf(lfo, 0.0f), 1.0f);
+                const float fc = exp10f(lfo * log_span + log_min);               // mapToLog10
+                const float g = tanf(w0 * fc);                                   // TPT prewarp
+                a.C[(int64_t)items[t] * a.n_ctl + j] = 2.0f * (g / (1.0f + g)) - 1.0f;
+            }
+        }
     }
 }
 
-// One sample of the cascade in "c form": out = c*in + (1-c)*s, s' = (1+c)*in - c*s per stage,
-// algebraically the TPT all-pass (v = G(in-s); y = v+s; s' = y+v; out = 2y-in) with c = 2G-1.
-__device__ __forceinline__ float cascade_step(float in, float (&s)[kStagesAP], float c, float omc, float opc) {
+// One sample of the cascade.  With c = 2G-1 the TPT all-pass (v = G(in-s); y = v+s; s' = y+v;
+// out = 2y-in) is out = s + c*(in-s), s' = in + c*(in-s): three instructions per stage.
+__device__ __forceinline__ float cascade_step(float in, float (&s)[kStagesAP], float c) {
     float v = in;
 #pragma unroll
     for (int k = 0; k < kStagesAP; ++k) {
-        const float o = fmaf(c, v, omc * s[k]);
-        s[k] = fmaf(opc, v, -c * s[k]);
+        const float d = v - s[k];
+        const float o = fmaf(c, d, s[k]);
+        s[k] = fmaf(c, d, v);
         v = o;
     }
     return v;
 }
 
 // ---- K1: per-chunk affine map ----------------------------------------------------------------
-// block = 256 threads = 32 chunks x 8 runs (7 unit states + the zero-state run driven by x)
+// block = 256 threads = 8 warps; warp r performs run r (0..6: unit state e_r, no input; 7: zero state,
+// driven by x) for 32 consecutive chunks, lane = chunk.  The run index is warp-uniform, so the
+// homogeneous warps never touch the audio.
+template <bool DRIVEN>
+__device__ __forceinline__ void map_run(const float (*xs)[kChunk + 1], const float (*cs)[kCtl + 1], int ch, int len,
+                                        float fbk, float (&s)[kStagesAP], float& out_prev, int j_begin) {
+    // out_prev holds the previous cascade output; lastOutput = out_prev * feedback
+    if (len == kChunk && j_begin == 0) {       // full chunk: no guards, one coefficient per 4 samples
+#pragma unroll 2
+        for (int g = 0; g < kCtl; ++g) {
+            const float c = cs[ch][g];
+#pragma unroll
+            for (int q = 0; q < kUpd; ++q) {
+                const float u = DRIVEN ? fmaf(-fbk, out_prev, xs[ch][g * kUpd + q]) : -fbk * out_prev;
+                out_prev = cascade_step(u, s, c);
+            }
+        }
+    } else {
+        for (int j = j_begin; j < len; ++j) {
+            const float c = cs[ch][j >> 2];
+            const float u = DRIVEN ? fmaf(-fbk, out_prev, xs[ch][j]) : -fbk * out_prev;
+            out_prev = cascade_step(u, s, c);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) phaser_map_kernel(const PhaserArgs a, int n_super) {
     __shared__ float xs[32][kChunk + 1];
     __shared__ float cs[32][kCtl + 1];
@@ -129,30 +172,29 @@ __global__ void __launch_bounds__(256) phaser_map_kernel(const PhaserArgs a, int
         cs[i / kCtl][i % kCtl] = (j < a.n_ctl) ? cr[j] : 0.0f;
     }
     __syncthreads();
-    const int ch = tid >> 3, run = tid & 7;
+    const int run = tid >> 5, ch = tid & 31;
     const int chunk = sc * 32 + ch;
     if (chunk >= a.n_chunks) return;
     const int len = min(kChunk, a.N - chunk * kChunk);
     const float fbk = a.feedback[b];
-    const float gate = (run == 7) ? 1.0f : 0.0f;
     float s[kStagesAP];
 #pragma unroll
     for (int k = 0; k < kStagesAP; ++k) s[k] = (run == k) ? 1.0f : 0.0f;
-    float last = (run == 6) ? 1.0f : 0.0f;
-    float c = 0.0f, omc = 1.0f, opc = 1.0f;
-    for (int j = 0; j < len; ++j) {
-        if ((j & (kUpd - 1)) == 0) {
-            c = cs[ch][j >> 2];
-            omc = 1.0f - c;
-            opc = 1.0f + c;
-        }
-        const float out = cascade_step(gate * xs[ch][j] - last, s, c, omc, opc);
-        last = out * fbk;
+    // state 6 is lastOutput = out_prev * feedback: a unit lastOutput is out_prev = 1 / feedback.  To stay
+    // finite for feedback = 0 the unit run carries `last` itself through the first sample.
+    float out_prev = 0.0f;
+    if (run == 7) {
+        map_run<true>(xs, cs, ch, len, fbk, s, out_prev, 0);
+    } else if (run == 6) {
+        out_prev = cascade_step(-1.0f, s, cs[ch][0]);       // first sample by hand: u = -lastOutput = -1
+        map_run<false>(xs, cs, ch, len, fbk, s, out_prev, 1);
+    } else {
+        map_run<false>(xs, cs, ch, len, fbk, s, out_prev, 0);
     }
     float* m = a.Mw + ((int64_t)item * a.n_chunks + chunk) * kMapFloats + run * kState;
 #pragma unroll
     for (int k = 0; k < kStagesAP; ++k) m[k] = s[k];
-    m[6] = last;
+    m[6] = out_prev * fbk;
 }
 
 // ---- K2: chain the maps: state at the start of every chunk --------------------------------------
@@ -165,69 +207,117 @@ __global__ void __launch_bounds__(256) phaser_scan_kernel(const PhaserArgs a) {
     const float* m = a.Mw + (int64_t)it * a.n_chunks * kMapFloats;
     float* S = a.S + (int64_t)it * a.n_chunks * kSFloats;
     const int ii = (i < kState) ? i : 0;
-    float s = 0.0f;
-#pragma unroll 4
-    for (int cidx = 0; cidx < a.n_chunks; ++cidx) {
-        if (live) S[cidx * kSFloats + i] = s;
-        const float* mc = m + (int64_t)cidx * kMapFloats;
-        float acc = mc[7 * kState + ii];                       // zero-state response
+    constexpr int kAhead = 4;                  // chunks of map coefficients in flight (they do not depend on s)
+    float buf[kAhead][8];
 #pragma unroll
-        for (int r = 0; r < kState; ++r) acc = fmaf(mc[r * kState + ii], __shfl_sync(kFull, s, r, 8), acc);
-        s = (i < kState) ? acc : 0.0f;
+    for (int d = 0; d < kAhead; ++d) {
+        const float* mc = m + (int64_t)min(d, a.n_chunks - 1) * kMapFloats;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) buf[d][r] = mc[r * kState + ii];
+    }
+    float s = 0.0f;
+    for (int c0 = 0; c0 < a.n_chunks; c0 += kAhead) {
+#pragma unroll
+        for (int d = 0; d < kAhead; ++d) {
+            const int cidx = c0 + d;
+            float cur[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) cur[r] = buf[d][r];
+            {   // refill this slot with chunk cidx + kAhead
+                const float* mc = m + (int64_t)min(cidx + kAhead, a.n_chunks - 1) * kMapFloats;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) buf[d][r] = mc[r * kState + ii];
+            }
+            if (cidx < a.n_chunks) {
+                if (live) S[cidx * kSFloats + i] = s;
+                float acc = cur[7];                                    // zero-state response
+#pragma unroll
+                for (int r = 0; r < kState; ++r) acc = fmaf(cur[r], __shfl_sync(kFull, s, r, 8), acc);
+                s = (i < kState) ? acc : 0.0f;
+            }
+        }
     }
 }
 
 // ---- K3: re-run every chunk from its true state, mix and clip --------------------------------------
-// block = 64 threads = 64 consecutive chunks of one example (8192 samples staged in shared memory)
-constexpr int kRunThreads = 64;
-__global__ void __launch_bounds__(kRunThreads) phaser_run_kernel(const PhaserArgs a, int n_super) {
-    extern __shared__ float sm[];
-    float(*xs)[kChunk + 1] = reinterpret_cast<float(*)[kChunk + 1]>(sm);
-    float(*cs)[kCtl + 1] = reinterpret_cast<float(*)[kCtl + 1]>(sm + kRunThreads * (kChunk + 1));
-    const int item = blockIdx.x / n_super, sc = blockIdx.x - item * n_super;
+// One thread per chunk; a warp owns 32 consecutive chunks (16 KB of audio).  The audio moves through a
+// per-warp 32 x 32 shared tile: row i is filled by one coalesced 128-byte request (all lanes read chunk
+// i), then lane i walks row i.  That keeps every global request at one cache line (a lane-per-chunk
+// access would touch 32 lines per request and saturate the L1 tag stage).
+constexpr int kRunWarps = 4;
+__global__ void __launch_bounds__(32 * kRunWarps) phaser_run_kernel(const PhaserArgs a) {
+    __shared__ float tile[kRunWarps][32][33];
+    __shared__ float ctile[kRunWarps][32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t wid = (int64_t)blockIdx.x * kRunWarps + w;          // warp id = group of 32 chunks of one example
+    const int groups = (a.n_chunks + 31) / 32;
+    if (wid >= (int64_t)a.n_items * groups) return;
+    const int item = (int)(wid / groups), grp = (int)(wid - (int64_t)item * groups);
     const int b = example_of(a, item);
-    const int tid = threadIdx.x;
-    const int n_base = sc * kRunThreads * kChunk;
+    const int chunk0 = grp * 32;
+    const int chunk = chunk0 + lane;
+    const bool live = chunk < a.n_chunks;
+    const int n_base = chunk0 * kChunk;                                // first sample of the warp's span
     const float* xr = a.x + (int64_t)b * a.N;
     float* yr = a.y + (int64_t)b * a.N;
-    for (int i = tid; i < kRunThreads * kChunk; i += kRunThreads) {
-        const int n = n_base + i;
-        xs[i / kChunk][i % kChunk] = (n < a.N) ? xr[n] : 0.0f;
-    }
     const float* cr = a.C + (int64_t)item * a.n_ctl;
-    for (int i = tid; i < kRunThreads * kCtl; i += kRunThreads) {
-        const int j = n_base / kUpd + i;
-        cs[i / kCtl][i % kCtl] = (j < a.n_ctl) ? cr[j] : 0.0f;
+    float(*t)[33] = tile[w];
+    float(*ct)[33] = ctile[w];
+    // coefficients of the 32 chunks: row i = chunk i's 32 control points
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+        const int j = (n_base >> 2) + i * kCtl + lane;
+        ct[i][lane] = (j < a.n_ctl) ? __ldg(cr + j) : 0.0f;
     }
-    __syncthreads();
-    const int chunk = sc * kRunThreads + tid;
-    if (chunk < a.n_chunks) {
-        const int len = min(kChunk, a.N - chunk * kChunk);
-        const float fbk = a.feedback[b];
-        const float wet = a.mix[b], dry = 1.0f - a.mix[b];
+    const float fbk = a.feedback[b];
+    const float wet = a.mix[b], dry = 1.0f - a.mix[b];
+    float s[kStagesAP];
+    float last = 0.0f;
+    if (live) {
         const float* S = a.S + ((int64_t)item * a.n_chunks + chunk) * kSFloats;
-        float s[kStagesAP];
 #pragma unroll
         for (int k = 0; k < kStagesAP; ++k) s[k] = S[k];
-        float last = S[6];
-        float c = 0.0f, omc = 1.0f, opc = 1.0f;
-        for (int j = 0; j < len; ++j) {
-            if ((j & (kUpd - 1)) == 0) {
-                c = cs[tid][j >> 2];
-                omc = 1.0f - c;
-                opc = 1.0f + c;
-            }
-            const float in = xs[tid][j];
-            const float out = cascade_step(in - last, s, c, omc, opc);
-            last = out * fbk;
-            const float o = dry * in + wet * out;
-            xs[tid][j] = fminf(fmaxf(o, -1.0f), 1.0f);          // datasets.py:472 clip
-        }
+        last = S[6];
+    } else {
+#pragma unroll
+        for (int k = 0; k < kStagesAP; ++k) s[k] = 0.0f;
     }
-    __syncthreads();
-    for (int i = tid; i < kRunThreads * kChunk; i += kRunThreads) {
-        const int n = n_base + i;
-        if (n < a.N) yr[n] = xs[i / kChunk][i % kChunk];
+    const int len = live ? min(kChunk, a.N - chunk * kChunk) : 0;
+    for (int q0 = 0; q0 < kChunk; q0 += 32) {                          // 4 sub-tiles of 32 samples
+        __syncwarp();
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int n = n_base + i * kChunk + q0 + lane;
+            t[i][lane] = (n < a.N) ? __ldg(xr + n) : 0.0f;
+        }
+        __syncwarp();
+        if (q0 + 32 <= len) {
+#pragma unroll 2
+            for (int g = 0; g < 8; ++g) {
+                const float c = ct[lane][(q0 >> 2) + g];
+#pragma unroll
+                for (int q = 0; q < kUpd; ++q) {
+                    const float in = t[lane][g * kUpd + q];
+                    const float out = cascade_step(in - last, s, c);
+                    last = out * fbk;
+                    t[lane][g * kUpd + q] = fminf(fmaxf(fmaf(wet, out, dry * in), -1.0f), 1.0f);   // datasets.py:472
+                }
+            }
+        } else {
+            for (int q = 0; q0 + q < len && q < 32; ++q) {
+                const float c = ct[lane][(q0 + q) >> 2];
+                const float in = t[lane][q];
+                const float out = cascade_step(in - last, s, c);
+                last = out * fbk;
+                t[lane][q] = fminf(fmaxf(fmaf(wet, out, dry * in), -1.0f), 1.0f);
+            }
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int n = n_base + i * kChunk + q0 + lane;
+            if (n < a.N) yr[n] = t[i][lane];
+        }
     }
 }
 
@@ -274,13 +364,7 @@ extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, 
     const int n_blocks = (int)((N + block - 1) / block);
     {
         const int total = a.n_items * n_blocks;
-        phaser_phase_kernel<<<(total + 63) / 64, 64, 0, s>>>(a, n_blocks);
-    }
-    {
-        int gx = (a.n_ctl + 255) / 256;
-        if (gx > 64) gx = 64;
-        MODFX_REQUIRE(a.n_items <= 65535, "n_items=%d exceeds grid.y", a.n_items);
-        phaser_coef_kernel<<<dim3(gx, a.n_items), 256, 0, s>>>(a);
+        phaser_ctl_kernel<<<(total + 31) / 32, kK0Threads, 0, s>>>(a, n_blocks);
     }
     {
         const int n_super = (a.n_chunks + 31) / 32;
@@ -288,10 +372,8 @@ extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, 
     }
     phaser_scan_kernel<<<(a.n_items * 8 + 255) / 256, 256, 0, s>>>(a);
     {
-        const int n_super = (a.n_chunks + kRunThreads - 1) / kRunThreads;
-        const size_t smem = sizeof(float) * (size_t)kRunThreads * ((kChunk + 1) + (kCtl + 1));
-        MODFX_CUDA_OK(cudaFuncSetAttribute(phaser_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        phaser_run_kernel<<<(unsigned)((int64_t)a.n_items * n_super), kRunThreads, smem, s>>>(a, n_super);
+        const int64_t warps = (int64_t)a.n_items * ((a.n_chunks + 31) / 32);
+        phaser_run_kernel<<<(unsigned)((warps + kRunWarps - 1) / kRunWarps), 32 * kRunWarps, 0, s>>>(a);
     }
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
