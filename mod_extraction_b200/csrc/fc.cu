@@ -22,7 +22,7 @@ constexpr int kTile = 128;          // samples per tile (4 sub-steps x 32 lanes)
 constexpr int kSub = kTile / kWarp; // 4
 constexpr int kLoWin = 512;         // control-rate LFO points staged in shared memory at a time
 constexpr int kStages = 8;          // dry-audio tiles in flight per warp (cp.async ring)
-constexpr int kMinWave = 6;         // below this dependency distance a block runs serially
+constexpr int kSerialMaxK = 7;      // register-history serial run covers tap distances up to this (+1)
 
 struct FcArgs {
     const float* x;
@@ -120,6 +120,35 @@ __device__ __forceinline__ void stage_tile(float* dst, const float* row, int n0,
     }
 }
 
+// ---- lock-step serial run over one full 32-sample block whose tap distances are all K or K+1 -------
+// Delays of a few samples make the recurrence truly serial: 4 dependent float ops per sample.  Every
+// lane executes the same code (no divergence): per sample one 16-byte broadcast read of the
+// pre-computed {x, fraction, 1-fraction, stale tap}, a 2-way select between history REGISTERS (the taps
+// are among the last K+1 values, so they never travel through shared memory on the critical path),
+// the 4 float ops of fx.py:113-114, and two stores (ring + interpolated value for the per-lane epilogue).
+template <int K>
+__device__ __noinline__ void serial_block(float* __restrict__ ring, int mask, int nb, const float4* __restrict__ coef,
+                                          unsigned sel_mask, float fb, float* __restrict__ it_out) {
+    float h[K + 2];
+#pragma unroll
+    for (int j = 1; j <= K + 1; ++j) h[j] = ring[(nb - j) & mask];
+    float* dst = ring + (nb & mask);            // blocks are 32-aligned and the ring is a multiple of 32: no wrap inside
+#pragma unroll
+    for (int i = 0; i < kWarp; ++i) {
+        const float4 cf = coef[i];
+        const bool sel = (sel_mask >> i) & 1u;  // tap p at distance K (else K+1)
+        const float vp = sel ? h[K] : h[K + 1];
+        const float vq = sel ? ((K == 1) ? cf.w : h[K - 1]) : h[K];
+        const float it = __fadd_rn(__fmul_rn(cf.y, vq), __fmul_rn(cf.z, vp));       // fx.py:113
+        const float v = __fadd_rn(cf.x, __fmul_rn(fb, it));                           // fx.py:114
+        dst[i] = v;
+        it_out[i] = it;
+#pragma unroll
+        for (int j = K + 1; j >= 2; --j) h[j] = h[j - 1];
+        h[1] = v;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -129,11 +158,13 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
     const int b = a.index ? a.index[item] : item;
     const int N = a.N;
 
-    // shared memory: [x stages][mod stages (audio-rate) | LFO window (control-rate)][ring]
+    // shared memory: [x stages][serial scratch][mod stages (audio-rate) | LFO window (control-rate)][ring]
     float* xst = smem;
-    float* mst = smem + kStages * kTile;
+    float4* coef = reinterpret_cast<float4*>(smem + kStages * kTile);       // 32 x {x, fr, omfr, stale}
+    float* itbuf = smem + kStages * kTile + 4 * kWarp;                      // 32 interpolated values
+    float* mst = itbuf + kWarp;
     float* lo = mst;
-    float* ring = smem + kStages * kTile + ((MODE == kAudioRate) ? kStages * kTile : ((MODE == kControlRate) ? kLoWin : 0));
+    float* ring = mst + ((MODE == kAudioRate) ? kStages * kTile : ((MODE == kControlRate) ? (kLoWin + 4) : 0));
 
     Coef c;
     c.M = a.M;
@@ -145,6 +176,9 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
     c.depth = a.depth_p ? a.depth_p[b] : a.depth_s;
     c.mix = a.mix_p ? a.mix_p[b] : a.mix_s;
     c.omm = a.mix_p ? __fsub_rn(1.0f, c.mix) : a.omm_s;                             // fx.py:117
+    // With 0 <= mod <= 1 and these bounds the delay stays in [0, M], so (w - d) + M lies in [0, 2M) and
+    // the reference's remainder is a single conditional subtraction (exact by Sterbenz).
+    const bool coef_ok = (c.A >= 0.0f) && (c.D0 >= 0.0f) && (__fadd_rn(c.A, c.D0) <= c.Mf) && (a.M >= kTile);
 
     const float* xs = a.x + ((int64_t)b * a.C + ch) * (int64_t)N;
     float* ys = a.y + ((int64_t)b * a.C + ch) * (int64_t)N;
@@ -168,11 +202,14 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
         lfo = make_lfo_desc(a.lfo_freq[b], a.lfo_phase[b], a.lfo_shape[b],
                             a.lfo_exp ? a.lfo_exp[b] : 1.0f, a.sr_lo);
     }
-    int lo_base = 0, lo_end = 0;    // control points [lo_base, lo_end) are staged in lo[]
+    int lo_base = 0, lo_end = 0;    // control points [lo_base, lo_end) are staged in lo[] (+1 duplicate at the end)
+    bool lo_ok = true;              // every staged control point lies in [0, 1]
     __syncwarp();
 
-    int w0 = 0;     // n0 mod M
-    int stage = 0;  // tile index mod kStages
+    int wk[kSub];                   // (n mod M) of this lane's sample in each 32-sample block of the tile
+#pragma unroll
+    for (int k = 0; k < kSub; ++k) wk[k] = (k * kWarp + lane) % c.M;
+    int stage = 0;                  // tile index mod kStages
     for (int n0 = 0; n0 < N; n0 += kTile) {
         {   // keep kStages-1 tiles of dry audio in flight
             int ps = stage + kStages - 1;
@@ -191,12 +228,15 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
                 __syncwarp();
                 lo_base = min((int)__fmul_rn(a.up_scale, (float)n0), a.n_lo - 1);
                 lo_end = min(lo_base + kLoWin, a.n_lo);
-                if (a.lfo_freq) {
-                    for (int i = lo_base + lane; i < lo_end; i += kWarp) lo[i - lo_base] = lfo_value(lfo, i);
-                } else {
-                    const float* src = a.mod + (int64_t)b * a.n_lo;
-                    for (int i = lo_base + lane; i < lo_end; i += kWarp) lo[i - lo_base] = src[i];
+                bool ok = true;
+                // one extra slot duplicates the last point so that tap i0+1 needs no clamp
+                for (int i = lo_base + lane; i <= lo_end; i += kWarp) {
+                    const int ii = min(i, a.n_lo - 1);
+                    const float v = a.lfo_freq ? lfo_value(lfo, ii) : a.mod[(int64_t)b * a.n_lo + ii];
+                    lo[i - lo_base] = v;
+                    ok = ok && (v >= 0.0f) && (v <= 1.0f);
                 }
+                lo_ok = __all_sync(kFull, ok);
             }
         }
         cp_async_wait<kStages - 1>();       // this tile's copies (issued kStages-1 tiles ago) landed
@@ -206,21 +246,58 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
         const float* mt = mst + stage * kTile;
         Samp s[kSub];
         bool indep = true;
+        bool fast = coef_ok && (n0 + kTile <= N) && (MODE != kControlRate || lo_ok);
+        if (fast) {
+            // ---- branch-free per-sample arithmetic of fx.py:95-102 (+ the x100 upsample) ----
+            const float* lo_shift = lo - lo_base;
+            bool bad = false;
 #pragma unroll
-        for (int k = 0; k < kSub; ++k) {
-            const int j = k * kWarp + lane;
-            const int n = n0 + j;
-            const bool valid = n < N;
-            int w = w0 + j;
-            if (w >= c.M) { w -= c.M; if (w >= c.M) w %= c.M; }
-            float m;
-            s[k].x = xt[j];
-            if (MODE == kAudioRate) m = mt[j];
-            else if (MODE == kControlRate) m = upsample_ac(lo - lo_base, a.n_lo, a.up_scale, min(n, N - 1));
-            else m = valid ? lfo_value(lfo, n) : 0.0f;
-            fc_index(m, w, c, s[k].fr, s[k].omfr, s[k].kp);
-            const int near = max(s[k].kp - 1, 1);          // = min(kp, kq)
-            indep = indep && (!valid || near > j);
+            for (int k = 0; k < kSub; ++k) {
+                const int j = k * kWarp + lane;
+                const int n = n0 + j;
+                s[k].x = xt[j];
+                float m;
+                if (MODE == kAudioRate) {
+                    m = mt[j];
+                    bad = bad || !(m >= 0.0f && m <= 1.0f);
+                } else if (MODE == kControlRate) {
+                    const float src = __fmul_rn(a.up_scale, (float)n);
+                    const int i0 = (int)src;
+                    const float l1 = __fsub_rn(src, (float)i0);
+                    const float l0 = __fsub_rn(1.0f, l1);
+                    m = __fmaf_rn(l0, lo_shift[i0], __fmul_rn(l1, lo_shift[i0 + 1]));
+                } else {
+                    m = lfo_value(lfo, n);
+                }
+                const float d = __fadd_rn(__fmul_rn(c.A, m), c.D0);                 // fx.py:98
+                const float t = __fadd_rn(__fsub_rn((float)wk[k], d), c.Mf);        // fx.py:99
+                const float r = (t >= c.Mf) ? __fsub_rn(t, c.Mf) : t;               // % M
+                const float pf = floorf(r);
+                s[k].fr = __fsub_rn(r, pf);                                          // fx.py:100
+                s[k].omfr = __fsub_rn(1.0f, s[k].fr);
+                int kp = wk[k] - (int)pf;                                            // fx.py:101
+                if (kp <= 0) kp += c.M;
+                s[k].kp = kp;
+                indep = indep && (kp >= ((j == 0) ? 1 : j + 2));                     // min(kp,kq) > j
+            }
+            if (MODE == kAudioRate && __any_sync(kFull, bad)) fast = false;          // mod outside [0,1]: exact remainder path
+        }
+        if (!fast) {
+            indep = true;
+#pragma unroll
+            for (int k = 0; k < kSub; ++k) {
+                const int j = k * kWarp + lane;
+                const int n = n0 + j;
+                const bool valid = n < N;
+                float m;
+                s[k].x = xt[j];
+                if (MODE == kAudioRate) m = mt[j];
+                else if (MODE == kControlRate) m = upsample_ac(lo - lo_base, a.n_lo, a.up_scale, min(n, N - 1));
+                else m = valid ? lfo_value(lfo, n) : 0.0f;
+                fc_index(m, wk[k], c, s[k].fr, s[k].omfr, s[k].kp);
+                const int near = max(s[k].kp - 1, 1);          // = min(kp, kq)
+                indep = indep && (!valid || near > j);
+            }
         }
 
         if (__all_sync(kFull, indep)) {
@@ -249,10 +326,11 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
                 if (cnt <= 0) break;
                 const Samp me = s[k];
                 const int n = nb + lane;
-                const int near = (lane < cnt) ? max(me.kp - 1, 1) : 0x7fffffff;
+                const bool mine = lane < cnt;
+                const int near = mine ? max(me.kp - 1, 1) : 0x7fffffff;
                 // smallest dependency distance relative to the block start, over the block
-                const int slack = __reduce_min_sync(kFull, (lane < cnt) ? (near - lane) : 0x7fffffff);
-                const int mn = __reduce_min_sync(kFull, near);
+                const int slack = __reduce_min_sync(kFull, mine ? (near - lane) : 0x7fffffff);
+                const int kmin = __reduce_min_sync(kFull, mine ? me.kp : 0x7fffffff);
                 float my_out = 0.0f;
                 if (slack > 0) {
                     // every sample depends only on samples before the block: one wave
@@ -261,66 +339,90 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
                     float v;
                     fc_sample(me, vp, vq, c, v, my_out);
                     __syncwarp();
-                    if (lane < cnt) ring[n & c.mask] = v;
-                } else if (mn >= kMinWave) {
-                    // waves of mn consecutive samples: sample j depends on samples <= j - mn
-                    for (int done = 0; done < cnt; done += mn) {
-                        if (lane >= done && lane < done + mn && lane < cnt) {
-                            const float vp = ring[(n - me.kp) & c.mask];
-                            const float vq = ring[(n - kq_of(me.kp, c.M)) & c.mask];
-                            float v;
-                            fc_sample(me, vp, vq, c, v, my_out);
-                            ring[n & c.mask] = v;
+                    if (mine) ring[n & c.mask] = v;
+                } else {
+                    const int kmax = __reduce_max_sync(kFull, mine ? me.kp : 0);
+                    if (cnt == kWarp && kmax - kmin <= 1 && kmin <= kSerialMaxK && c.M >= 2 * kWarp) {
+                        // ---- delays of K..K+1 samples: register-history serial run ----
+                        const float stale = ring[(n - c.M) & c.mask];        // tap q of a sub-sample delay (kp == 1)
+                        coef[lane] = make_float4(me.x, me.fr, me.omfr, stale);
+                        const unsigned sel = __ballot_sync(kFull, me.kp == kmin);
+                        __syncwarp();
+                        switch (kmin) {
+                            case 1: serial_block<1>(ring, c.mask, nb, coef, sel, c.fb, itbuf); break;
+                            case 2: serial_block<2>(ring, c.mask, nb, coef, sel, c.fb, itbuf); break;
+                            case 3: serial_block<3>(ring, c.mask, nb, coef, sel, c.fb, itbuf); break;
+                            case 4: serial_block<4>(ring, c.mask, nb, coef, sel, c.fb, itbuf); break;
+                            case 5: serial_block<5>(ring, c.mask, nb, coef, sel, c.fb, itbuf); break;
+                            case 6: serial_block<6>(ring, c.mask, nb, coef, sel, c.fb, itbuf); break;
+                            default: serial_block<7>(ring, c.mask, nb, coef, sel, c.fb, itbuf); break;
                         }
                         __syncwarp();
-                    }
-                } else {
-                    // ---- delays of a few samples: lock-step serial run over the block.  All
-                    // lanes compute every sample (no divergence); taps at distance 1 and 2 are
-                    // forwarded from registers, older taps are loaded two samples ahead so the
-                    // shared-memory latency stays off the recurrence's critical path. ----
-                    float p1 = ring[(nb - 1) & c.mask];
-                    float p2 = ring[(nb - 2) & c.mask];
-                    int kpa = __shfl_sync(kFull, me.kp, 0);
-                    int kpb = __shfl_sync(kFull, me.kp, 1);
-                    float lpa = ring[(nb - kpa) & c.mask];
-                    float lqa = ring[(nb - kq_of(kpa, c.M)) & c.mask];
-                    float lpb = ring[(nb + 1 - kpb) & c.mask];
-                    float lqb = ring[(nb + 1 - kq_of(kpb, c.M)) & c.mask];
-                    float my_it = 0.0f;
+                        const float it = itbuf[lane];
+                        const float o = __fadd_rn(me.x, __fmul_rn(c.depth, it));                 // fx.py:115
+                        const float r = __fadd_rn(__fmul_rn(c.omm, me.x), __fmul_rn(c.mix, o));  // fx.py:117
+                        my_out = fminf(fmaxf(r, -1.0f), 1.0f);
+                    } else if (kmin >= 3) {
+                        // waves of mn consecutive samples: sample j depends on samples <= j - mn
+                        const int mn = kmin - 1;
+                        for (int done = 0; done < cnt; done += mn) {
+                            if (lane >= done && lane < done + mn && mine) {
+                                const float vp = ring[(n - me.kp) & c.mask];
+                                const float vq = ring[(n - kq_of(me.kp, c.M)) & c.mask];
+                                float v;
+                                fc_sample(me, vp, vq, c, v, my_out);
+                                ring[n & c.mask] = v;
+                            }
+                            __syncwarp();
+                        }
+                    } else {
+                        // ---- anything else with a 1-2 sample delay in it (irregular modulation): generic
+                        // lock-step serial run; taps at distance 1 and 2 come from registers, older taps are
+                        // loaded two samples ahead. ----
+                        float p1 = ring[(nb - 1) & c.mask];
+                        float p2 = ring[(nb - 2) & c.mask];
+                        int kpa = __shfl_sync(kFull, me.kp, 0);
+                        int kpb = __shfl_sync(kFull, me.kp, 1);
+                        float lpa = ring[(nb - kpa) & c.mask];
+                        float lqa = ring[(nb - kq_of(kpa, c.M)) & c.mask];
+                        float lpb = ring[(nb + 1 - kpb) & c.mask];
+                        float lqb = ring[(nb + 1 - kq_of(kpb, c.M)) & c.mask];
+                        float my_it = 0.0f;
 #pragma unroll 4
-                    for (int i = 0; i < cnt; ++i) {
-                        // taps of sample i+2 (valid when their distance is >= 3: already stored)
-                        const int kpc = __shfl_sync(kFull, me.kp, (i + 2) & 31);
-                        const float lpc = ring[(nb + i + 2 - kpc) & c.mask];
-                        const float lqc = ring[(nb + i + 2 - kq_of(kpc, c.M)) & c.mask];
-                        const float xi = __shfl_sync(kFull, me.x, i);
-                        const float fri = __shfl_sync(kFull, me.fr, i);
-                        const float omi = __shfl_sync(kFull, me.omfr, i);
-                        const int kqa = kq_of(kpa, c.M);
-                        const float vp = (kpa == 1) ? p1 : ((kpa == 2) ? p2 : lpa);
-                        const float vq = (kqa == 1) ? p1 : ((kqa == 2) ? p2 : lqa);
-                        const float it = __fadd_rn(__fmul_rn(fri, vq), __fmul_rn(omi, vp));     // fx.py:113
-                        const float v = __fadd_rn(xi, __fmul_rn(c.fb, it));                      // fx.py:114
-                        ring[(nb + i) & c.mask] = v;        // every lane stores the same value
-                        if (lane == i) my_it = it;
-                        p2 = p1; p1 = v;
-                        kpa = kpb; lpa = lpb; lqa = lqb;
-                        kpb = kpc; lpb = lpc; lqb = lqc;
-                    }
-                    {   // per-lane output of fx.py:115-118 from the stored interpolated value
+                        for (int i = 0; i < cnt; ++i) {
+                            // taps of sample i+2 (valid when their distance is >= 3: already stored)
+                            const int kpc = __shfl_sync(kFull, me.kp, (i + 2) & 31);
+                            const float lpc = ring[(nb + i + 2 - kpc) & c.mask];
+                            const float lqc = ring[(nb + i + 2 - kq_of(kpc, c.M)) & c.mask];
+                            const float xi = __shfl_sync(kFull, me.x, i);
+                            const float fri = __shfl_sync(kFull, me.fr, i);
+                            const float omi = __shfl_sync(kFull, me.omfr, i);
+                            const int kqa = kq_of(kpa, c.M);
+                            const float vp = (kpa == 1) ? p1 : ((kpa == 2) ? p2 : lpa);
+                            const float vq = (kqa == 1) ? p1 : ((kqa == 2) ? p2 : lqa);
+                            const float it = __fadd_rn(__fmul_rn(fri, vq), __fmul_rn(omi, vp));     // fx.py:113
+                            const float v = __fadd_rn(xi, __fmul_rn(c.fb, it));                      // fx.py:114
+                            ring[(nb + i) & c.mask] = v;        // every lane stores the same value
+                            if (lane == i) my_it = it;
+                            p2 = p1; p1 = v;
+                            kpa = kpb; lpa = lpb; lqa = lqb;
+                            kpb = kpc; lpb = lpc; lqb = lqc;
+                        }
                         const float o = __fadd_rn(me.x, __fmul_rn(c.depth, my_it));
                         const float r = __fadd_rn(__fmul_rn(c.omm, me.x), __fmul_rn(c.mix, o));
                         my_out = fminf(fmaxf(r, -1.0f), 1.0f);
                     }
                 }
-                if (lane < cnt) ys[n] = my_out;
+                if (mine) ys[n] = my_out;
                 __syncwarp();
             }
         }
         __syncwarp();
-        w0 += kTile;
-        if (w0 >= c.M) { w0 -= c.M; if (w0 >= c.M) w0 %= c.M; }
+#pragma unroll
+        for (int k = 0; k < kSub; ++k) {
+            wk[k] += kTile;
+            if (wk[k] >= c.M) { wk[k] -= c.M; if (wk[k] >= c.M) wk[k] %= c.M; }
+        }
         if (++stage == kStages) stage = 0;
     }
     cp_async_wait<0>();
@@ -462,8 +564,8 @@ extern "C" int modfx_flanger_chorus_f32(const float* x, float* y, int32_t B, int
     if (a.n_items == 0) return MODFX_OK;
     MODFX_REQUIRE(a.n_items > 0, "n_items=%d", a.n_items);
 
-    const size_t smem = sizeof(float) * ((size_t)ring + (size_t)kStages * kTile +
-                                         (mode == kAudioRate ? (size_t)kStages * kTile : (mode == kControlRate ? (size_t)kLoWin : 0)));
+    const size_t smem = sizeof(float) * ((size_t)ring + (size_t)kStages * kTile + 5 * kWarp +
+                                         (mode == kAudioRate ? (size_t)kStages * kTile : (mode == kControlRate ? (size_t)kLoWin + 4 : 0)));
     if (smem > 200 * 1024)
         return fail(MODFX_ERR_UNSUPPORTED, "delay line of %d samples (+%d control points) needs %zu B of shared memory",
                     a.M, a.n_lo, smem);

@@ -112,6 +112,40 @@ def test_flanger_worst_case_serial_delays():
     assert np.array_equal(y.cpu().numpy(), ref)
 
 
+def test_flanger_every_schedule_of_the_kernel():
+    """Constant delays of 0.5 .. 9.5, 31.5, 32.5, 127.5, 128.5 samples and slow ramps across those
+    boundaries: exercises the register-history serial run for every tap distance K, the wave
+    schedule, the one-wave block and the 128-sample tile, plus the transitions between them."""
+    from mod_extraction_b200.fx import MonoFlangerChorusModule
+    N = 12000
+    delays = [0.0, 0.5, 1.0, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5, 8.5, 9.5, 15.25, 31.5, 32.5, 64.0, 127.5, 128.5, 300.0]
+    ramps = [(0.0, 12.0), (12.0, 0.0), (6.0, 40.0), (140.0, 20.0), (0.0, 484.0)]
+    B = len(delays) + len(ramps)
+    x = white((B, 1, N), 77)
+    mod = np.zeros((B, N), dtype=np.float32)
+    for i, d in enumerate(delays):
+        mod[i] = d / 441.0
+    t = np.linspace(0.0, 1.0, N)
+    for i, (d0, d1) in enumerate(ramps):
+        mod[len(delays) + i] = (d0 + (d1 - d0) * t) / 441.0
+    rng = np.random.RandomState(5)
+    fb = rng.uniform(0.3, 0.69, B).astype(np.float32)
+    zeros, ones = np.zeros(B, dtype=np.float32), np.ones(B, dtype=np.float32)
+    params = [fb, zeros, ones, ones * 0.8, ones * 0.9]          # min_delay_width = 0: delay = 441 * mod
+    ref = oracle.flanger_chorus(x, mod, *params, max_min_delay_ms=1.0, max_lfo_delay_ms=10.0)
+    m = MonoFlangerChorusModule(B, 1, N, SR, 1.0, 10.0)
+    y = m(torch.from_numpy(x).to(dev()), torch.from_numpy(mod).to(dev()), *[to_t(p) for p in params]).cpu().numpy()
+    for i in range(B):
+        assert np.array_equal(y[i], ref[i]), (i, (delays + ramps)[i])
+    # same through the control-rate path (delays now follow the x100 upsample of 120 control points)
+    lo = mod[:, ::100].copy()
+    ref2 = oracle.flanger_chorus(x, oracle.linear_interpolate_last_dim(lo, N), *params, max_min_delay_ms=1.0,
+                                 max_lfo_delay_ms=10.0)
+    y2 = m.forward_control_rate(torch.from_numpy(x).to(dev()), torch.from_numpy(lo).to(dev()),
+                                *[to_t(p) for p in params]).cpu().numpy()
+    assert np.array_equal(y2, ref2)
+
+
 @pytest.mark.parametrize("N", [1, 31, 32, 33, 127, 128, 129, 485, 1000])
 def test_flanger_ragged_lengths(N):
     from mod_extraction_b200.fx import MonoFlangerChorusModule
