@@ -168,16 +168,21 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
                 im[n2] = Ei[lane * kEStride + n2];
             }
             fft_dif<32>(re, im);
-            // ---- real-FFT split + power: this lane owns bins k = k1 + 16 k2 of its frame
+            // ---- real-FFT split + power.  Bins k and 512-k share all their intermediate terms
+            // (X[512-k] uses the same sums / differences with two signs flipped), so each pair is
+            // computed once: this lane handles its own bins k = k1 + 16 k2 for k2 < 16 together with the
+            // mirror bins 512-k, which belong to the partner lane (f, 16-k1) at k2' = 31-k2.
             constexpr float C64[32] = MODFX_C64;
             constexpr float S64[32] = MODFX_S64;
             const int f = lane >> 4, k1 = lane & 15;
             const int partner = (lane & 16) | ((16 - k1) & 15);
+            const int k1m = (16 - k1) & 15;                 // k1 of the mirror bins
             // the two 16-byte halves of a power row are swapped on every other group of 4 rows so that
             // rows r and r+4 (same banks) are read / written through different banks
-            float* Pcol = P + ((lf + f) ^ (((k1 >> 2) & 1) << 2));
+            float* Pown = P + ((lf + f) ^ (((k1 >> 2) & 1) << 2));
+            float* Pmir = P + ((lf + f) ^ (((k1m >> 2) & 1) << 2));
 #pragma unroll
-            for (int k2 = 0; k2 < 32; ++k2) {
+            for (int k2 = 0; k2 < 16; ++k2) {
                 const int own = BitRev<32>::of(k2);
                 const int src_other = BitRev<32>::of(31 - k2);          // Z[512-k] lives in the partner lane
                 const int src_self = BitRev<32>::of((32 - k2) & 31);    // ... or in this lane when k1 == 0
@@ -189,11 +194,26 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
                 }
                 const float c = c1 * C64[k2] - s1 * S64[k2];            // cos(2 pi k / 1024)
                 const float s = s1 * C64[k2] + c1 * S64[k2];
-                Pcol[(k1 + 16 * k2) * kPStride] = rfft_split_power(re[own], im[own], pr, pi, c, s);
+                const float zr = re[own], zi = im[own];
+                const float ar = zr + pr, ai = zi - pi;                 // Z[k] + conj Z[512-k]
+                const float br = zr - pr, bi = zi + pi;                 // Z[k] - conj Z[512-k]
+                const float t1 = c * bi - s * br;
+                const float t2 = c * br + s * bi;
+                const float xr = ar + t1, xi = ai - t2;                 // 2 X[k]
+                const float yr = ar - t1, yi = ai + t2;                 // 2 conj-ish X[512-k] (same magnitude)
+                Pown[(k1 + 16 * k2) * kPStride] = 0.25f * (xr * xr + xi * xi);
+                // mirror bin index: 512 - k = k1m + 16 (31 - k2) for k1 != 0, 16 (32 - k2) for k1 == 0
+                const int km = (k1 == 0) ? 16 * (32 - k2) : (k1m + 16 * (31 - k2));
+                if (!(k1 == 0 && k2 == 0)) Pmir[km * kPStride] = 0.25f * (yr * yr + yi * yi);
             }
             if (k1 == 0) {
-                const float v = re[0] - im[0];          // X[512] = Re Z[0] - Im Z[0]
-                Pcol[512 * kPStride] = v * v;
+                // k = 0 was written above (X[0] = Re Z[0] + Im Z[0]); Nyquist and the self-paired k = 256
+                const float v = re[0] - im[0];                          // X[512] = Re Z[0] - Im Z[0]
+                Pown[512 * kPStride] = v * v;
+                const int own = BitRev<32>::of(16);                     // Z[256]: its own mirror
+                const float zr = re[own], zi = im[own];
+                // A = (2 zr, 0), B = (0, 2 zi), (c, s) = (cos, sin)(pi/2) = (0, 1):  X[256] = (zr, -zi)
+                Pown[256 * kPStride] = zr * zr + zi * zi;
             }
         }
         __syncthreads();
@@ -214,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
 #pragma unroll
                     for (int t = 0; t < kFB; ++t) acc[t] = 0.0f;
                     const int r0 = (int)mstart[m];
+#pragma unroll 2
                     for (int j = 0; j < cnt; ++j) {
                         const float wj = w[j];
                         const int r = r0 + j;
