@@ -9,7 +9,10 @@ import ctypes
 import os
 from typing import Optional
 
-from ._build import LIB_PATH
+from ._build import LIB_PATH as _DEFAULT_LIB_PATH
+
+# MODFX_LIB points the loader at an alternative build of the same ABI (kernel experiments)
+LIB_PATH = os.environ.get("MODFX_LIB", _DEFAULT_LIB_PATH)
 
 c_f32p = ctypes.POINTER(ctypes.c_float)
 c_i32p = ctypes.POINTER(ctypes.c_int32)

@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
         }
         __syncthreads();
 
+#ifndef MODFX_EXP_SKIP_MEL
         // ---- banded mel projection + clip + log.  A thread owns whole mel bands (a low one and its
         // mirror from the top, so the 1..14 taps balance) and all 8 frames of the iteration: per tap
         // one weight, two 16-byte reads of the power row, eight FMAs.
@@ -246,14 +247,31 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
                         acc[4] = fmaf(wj, p1.x, acc[4]); acc[5] = fmaf(wj, p1.y, acc[5]);
                         acc[6] = fmaf(wj, p1.z, acc[6]); acc[7] = fmaf(wj, p1.w, acc[7]);
                     }
-                    float* op = orow + (int64_t)m * a.n_frames + t0;
-                    const int live = min(kFB, a.n_frames - t0);
-#pragma unroll
-                    for (int t = 0; t < kFB; ++t)
-                        if (t < live) op[t] = a.apply_log ? __logf(fmaxf(acc[t], a.eps)) : acc[t];
+                    // results go through shared memory (the idle FFT exchange buffer) so that the global
+                    // stores below are 32-byte segments instead of 4-byte scatters
+                    float4 o0, o1;
+                    if (a.apply_log) {
+                        o0 = make_float4(__logf(fmaxf(acc[0], a.eps)), __logf(fmaxf(acc[1], a.eps)),
+                                         __logf(fmaxf(acc[2], a.eps)), __logf(fmaxf(acc[3], a.eps)));
+                        o1 = make_float4(__logf(fmaxf(acc[4], a.eps)), __logf(fmaxf(acc[5], a.eps)),
+                                         __logf(fmaxf(acc[6], a.eps)), __logf(fmaxf(acc[7], a.eps)));
+                    } else {
+                        o0 = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        o1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    }
+                    reinterpret_cast<float4*>(E)[2 * m] = o0;
+                    reinterpret_cast<float4*>(E)[2 * m + 1] = o1;
                 }
             }
+            __syncthreads();
+            // 8 consecutive lanes write the 8 frames of one band: one 32-byte segment per band row
+            const int live = min(kFB, a.n_frames - t0);
+            for (int idx = tid; idx < a.n_mels * kFB; idx += kThreads) {
+                const int m = idx >> 3, t = idx & (kFB - 1);
+                if (t < live) orow[(int64_t)m * a.n_frames + t0 + t] = E[idx];
+            }
         }
+#endif
         // no barrier here: the next iteration's first barrier orders this read of P before the next write
         // (P is only written after the barrier that follows pass 1)
     }
@@ -277,7 +295,7 @@ extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T
     MODFX_REQUIRE(T > n_fft / 2, "reflect padding needs T > n_fft/2 (T=%lld)", (long long)T);   // torch raises too
     MODFX_REQUIRE(T < (1ll << 30), "T too long");
     MODFX_REQUIRE(n_mels >= 1 && fb_stride >= 1 && fb_taps >= 1, "bad mel table");
-    if (n_mels > 4096 || fb_taps > 8192 || (int64_t)n_mels * 0 + fb_taps > 65535)
+    if (n_mels * kFB > kWarps * 2 * 32 * kEStride || fb_taps > 8192)
         return fail(MODFX_ERR_UNSUPPORTED, "mel table too large for shared memory (n_mels=%d taps=%d)", n_mels, fb_taps);
     if (row_index) R = n_index;
     if (R <= 0) return MODFX_OK;
