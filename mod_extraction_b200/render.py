@@ -46,19 +46,22 @@ class InterwovenRenderer:
         self._idx_cache: Dict[int, Tuple[Tensor, ...]] = {}
 
     # ------------------------------------------------------------------ helpers
-    def _groups(self, effect: Tensor):
-        key = id(effect)
+    def _groups(self, effect: Tensor, lo: int = 0, hi: Optional[int] = None):
+        """Index lists (relative to `lo`) of the flanger / chorus / phaser examples in effect[lo:hi]."""
+        hi = effect.numel() if hi is None else hi
+        key = (id(effect), lo, hi)
         hit = self._idx_cache.get(key)
         if hit is not None and hit[0] is effect:
             return hit[1:]
-        e = effect.detach().cpu()
+        e = effect.detach().cpu()[lo:hi]
         groups = []
         for k in (FLANGER, CHORUS, PHASER):
             idx = torch.nonzero(e == k).reshape(-1).to(torch.int32)
             groups.append(idx.to(self.device))
-        B = e.numel()
-        dry_rows = torch.arange(B, dtype=torch.int32, device=self.device)
-        self._idx_cache = {key: (effect, *groups, dry_rows)}
+        dry_rows = torch.arange(hi - lo, dtype=torch.int32, device=self.device)
+        if len(self._idx_cache) > 64:
+            self._idx_cache.clear()
+        self._idx_cache[key] = (effect, *groups, dry_rows)
         return (*groups, dry_rows)
 
     def alloc_outputs(self, B: int) -> Tuple[Tensor, Tensor]:
@@ -68,8 +71,62 @@ class InterwovenRenderer:
 
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
+    def render_host(self, dry_h: Tensor, effect: Tensor, mod_lo_h: Tensor, fc_h: Dict[str, Tensor],
+                    ph_h: Dict[str, Tensor], wet_h: Tensor, logmel: Tensor, stat_h: Optional[Tensor] = None,
+                    chunk: int = 512, dry_d: Optional[Tensor] = None, wet_d: Optional[Tensor] = None) -> None:
+        """Host-buffer entry point: pinned host dry audio + parameters in, wet audio out to the pinned host
+        tensor `wet_h`; the log-mel tensor stays on the GPU (`logmel`, (B,2,n_mels,n_frames)) where the
+        extractor consumes it, and `stat_h` (B, 2) receives its per-example mean.  The batch is cut into
+        chunks so that the H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1
+        overlap (PCIe is full duplex); the call returns when everything has landed."""
+        B, _, N = dry_h.shape
+        if dry_d is None:
+            dry_d = torch.empty((B, 1, N), device=self.device, dtype=torch.float32)
+        if wet_d is None:
+            wet_d = torch.empty((B, 1, N), device=self.device, dtype=torch.float32)
+        if not hasattr(self, "_io_streams"):
+            self._io_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        s_in, s_run, s_out = self._io_streams
+        cur = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(cur)
+        for st in self._io_streams:
+            st.wait_event(start)
+        fc_keys = ("feedback", "min_delay_width", "width", "depth", "mix")
+        ph_keys = ("rate_hz", "depth", "centre_frequency_hz", "feedback", "mix")
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            with torch.cuda.stream(s_in):
+                dry_d[lo:hi].copy_(dry_h[lo:hi], non_blocking=True)
+                m = mod_lo_h[lo:hi].to(self.device, non_blocking=True)
+                f = {k: fc_h[k][lo:hi].to(self.device, non_blocking=True) for k in fc_keys}
+                p = {k: ph_h[k][lo:hi].to(self.device, non_blocking=True) for k in ph_keys}
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            s_run.wait_event(ev_in)
+            with torch.cuda.stream(s_run):
+                self.render(dry_d[lo:hi], effect, m, f, p, wet=wet_d[lo:hi], logmel=logmel[lo:hi], _range=(lo, hi))
+                st_d = logmel[lo:hi].mean(dim=(2, 3)) if stat_h is not None else None
+                ev_run = torch.cuda.Event()
+                ev_run.record(s_run)
+                for t in (m, *f.values(), *p.values()):
+                    t.record_stream(s_run)
+            s_out.wait_event(ev_run)
+            with torch.cuda.stream(s_out):
+                wet_h[lo:hi].copy_(wet_d[lo:hi], non_blocking=True)
+                if stat_h is not None:
+                    stat_h[lo:hi].copy_(st_d, non_blocking=True)
+                    st_d.record_stream(s_out)
+        for st in self._io_streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+        cur.synchronize()
+
+    @torch.no_grad()
     def render(self, dry: Tensor, effect: Tensor, mod_lo: Tensor, fc: Dict[str, Tensor], ph: Dict[str, Tensor],
-               wet: Optional[Tensor] = None, logmel: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+               wet: Optional[Tensor] = None, logmel: Optional[Tensor] = None,
+               _range: Optional[Tuple[int, int]] = None) -> Tuple[Tensor, Tensor]:
         """dry (B,1,N) CUDA float32; effect (B,) ints in {0: flanger, 1: chorus, 2: phaser};
         mod_lo (B, n_lo) control-rate LFO of the flanger / chorus examples (rows of phaser examples are
         ignored); fc: feedback, min_delay_width, width, depth, mix as (B,) tensors (data_modules.py:421-445);
@@ -83,7 +140,7 @@ class InterwovenRenderer:
             w2, l2 = self.alloc_outputs(B)
             wet = w2 if wet is None else wet
             logmel = l2 if logmel is None else logmel
-        i_fl, i_ch, i_ph, _ = self._groups(effect)
+        i_fl, i_ch, i_ph, _ = self._groups(effect) if _range is None else self._groups(effect, *_range)
         fc_args = [fc[k] for k in ("feedback", "min_delay_width", "width", "depth", "mix")]
         ph_args = [ph[k] for k in ("rate_hz", "depth", "centre_frequency_hz", "feedback", "mix")]
         src = ModSource.control_rate(mod_lo)
