@@ -268,7 +268,11 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
             const int live = min(kFB, a.n_frames - t0);
             for (int idx = tid; idx < a.n_mels * kFB; idx += kThreads) {
                 const int m = idx >> 3, t = idx & (kFB - 1);
+#ifdef MODFX_EXP_NO_STORE
+                if (t < live && E[idx] == 12345.678f) orow[(int64_t)m * a.n_frames + t0 + t] = E[idx];
+#else
                 if (t < live) orow[(int64_t)m * a.n_frames + t0 + t] = E[idx];
+#endif
             }
         }
 #endif
