@@ -65,3 +65,12 @@ def test_reference_asserts_are_kept():
         m(x[:, 0], torch.zeros(2, 64))                 # fx.py:80
     with pytest.raises(AssertionError):
         fx.apply_tremolo(x, torch.zeros(2, 64), mix=1.5)           # fx.py:21
+
+
+def test_torch_ops_registered_cuda_only():
+    """torch.ops.modfx.* exist and have no CPU kernel: the dispatcher itself refuses CPU tensors."""
+    import torch
+    import mod_extraction_b200._torch_ops  # noqa: F401
+    assert hasattr(torch.ops.modfx, "flanger_chorus") and hasattr(torch.ops.modfx, "phaser")
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.modfx.interp_linear(torch.zeros(2, 8), 16, True)

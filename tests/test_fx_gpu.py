@@ -330,3 +330,10 @@ def test_full_size_properties_config3():
     ref = oracle.flanger_chorus(x[rows].numpy(), oracle.linear_interpolate_last_dim(lo[rows].numpy(), N),
                                 *[p[rows] for p in params], max_min_delay_ms=1.0, max_lfo_delay_ms=10.0)
     assert np.array_equal(y[rows].cpu().numpy(), ref)
+
+
+def test_torch_ops_dispatch_on_cuda():
+    import mod_extraction_b200._torch_ops  # noqa: F401
+    x = torch.rand(3, 50, device=dev())
+    y = torch.ops.modfx.interp_linear(x, 120, True)
+    assert np.array_equal(y.cpu().numpy(), oracle.linear_interpolate_last_dim(x.cpu().numpy(), 120))
