@@ -69,12 +69,10 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
     const int span = (kFB - 1) * a.hop + kNfft;      // samples staged per iteration
 
     float* win = smem;                         // [1024]
-    float* tw1c = win + kNfft;                 // [16][32]  cos(-2 pi n2 k1 / 512)
-    float* tw1s = tw1c + 512;
-    float* P = tw1s + 512;                     // [513][8]
-    float* E = P + kBins * kPStride + 4;       // per warp: Er[32][33], Ei[32][33]  (kBins*8 + 4 keeps 16 B alignment)
-    float* Er = E + warp * (2 * 32 * kEStride);
-    float* Ei = Er + 32 * kEStride;
+    float2* tw1 = reinterpret_cast<float2*>(win + kNfft);       // [16][32]  exp(-2 pi i n2 k1 / 512) as (cos, sin)
+    float* P = win + kNfft + 2 * 512;          // [513][8]
+    float* E = P + kBins * kPStride + 4;       // per warp: float2 Ew[32][33]  (kBins*8 + 4 keeps 16 B alignment)
+    float2* Ew = reinterpret_cast<float2*>(E) + warp * (32 * kEStride);
     float* sbuf = E + kWarps * (2 * 32 * kEStride);             // [span rounded up to 4]
     float* melw = sbuf + ((span + 3) & ~3);                     // [fb_taps] band weights, bands back to back
     unsigned short* moff = reinterpret_cast<unsigned short*>(melw + a.fb_taps);    // [n_mels + 1] first weight of band m
@@ -85,8 +83,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
         const int k1 = i >> 5, n2 = i & 31;
         float s, c;
         sincospif(-(float)(n2 * k1) / 256.0f, &s, &c);
-        tw1c[i] = c;
-        tw1s[i] = s;
+        tw1[i] = make_float2(c, s);
     }
     // compact copy of the banded mel table (<= 14 taps per band for the reference configuration)
     if (tid == 0) {
@@ -127,27 +124,24 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
 
         const int lf = 2 * warp;                        // local index of this warp's first frame
         const bool active = t0 + lf < a.n_frames;
-        float re[32], im[32];
+        float2 v[32];
         if (active) {
             // ---- pass 1: lane = n2; 16-point FFT over n1 of z[32 n1 + n2], both frames
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
-                float r16[16], i16[16];
+                float2 u[16];
                 const float* fr = sbuf + (lf + f) * a.hop;
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) {
-                    const float2 v = *reinterpret_cast<const float2*>(fr + 64 * n1 + 2 * lane);
-                    const float2 w = *reinterpret_cast<const float2*>(win + 64 * n1 + 2 * lane);
-                    r16[n1] = v.x * w.x;
-                    i16[n1] = v.y * w.y;
+                    const float2 x2 = *reinterpret_cast<const float2*>(fr + 64 * n1 + 2 * lane);
+                    const float2 w2 = *reinterpret_cast<const float2*>(win + 64 * n1 + 2 * lane);
+                    u[n1] = c_mul2(x2, w2);
                 }
-                fft_dif<16>(r16, i16);
+                fft_dif<16>(u);
 #pragma unroll
                 for (int k1 = 0; k1 < 16; ++k1) {
-                    const float yr = r16[BitRev<16>::of(k1)], yi = i16[BitRev<16>::of(k1)];
-                    const float c = tw1c[k1 * 32 + lane], s = tw1s[k1 * 32 + lane];
-                    Er[(f * 16 + k1) * kEStride + lane] = yr * c - yi * s;
-                    Ei[(f * 16 + k1) * kEStride + lane] = yr * s + yi * c;
+                    const float2 t = tw1[k1 * 32 + lane];
+                    Ew[(f * 16 + k1) * kEStride + lane] = c_mul_tw(u[BitRev<16>::of(k1)], t.x, t.y);
                 }
             }
         }
@@ -163,11 +157,8 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
         if (active) {
             // ---- pass 2: lane = (frame f, k1); 32-point FFT over n2
 #pragma unroll
-            for (int n2 = 0; n2 < 32; ++n2) {
-                re[n2] = Er[lane * kEStride + n2];
-                im[n2] = Ei[lane * kEStride + n2];
-            }
-            fft_dif<32>(re, im);
+            for (int n2 = 0; n2 < 32; ++n2) v[n2] = Ew[lane * kEStride + n2];
+            fft_dif<32>(v);
             // ---- real-FFT split + power.  Bins k and 512-k share all their intermediate terms
             // (X[512-k] uses the same sums / differences with two signs flipped), so each pair is
             // computed once: this lane handles its own bins k = k1 + 16 k2 for k2 < 16 together with the
@@ -186,34 +177,23 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
                 const int own = BitRev<32>::of(k2);
                 const int src_other = BitRev<32>::of(31 - k2);          // Z[512-k] lives in the partner lane
                 const int src_self = BitRev<32>::of((32 - k2) & 31);    // ... or in this lane when k1 == 0
-                float pr = __shfl_sync(kFull, re[src_other], partner);
-                float pi = __shfl_sync(kFull, im[src_other], partner);
-                if (k1 == 0) {
-                    pr = re[src_self];
-                    pi = im[src_self];
-                }
-                const float c = c1 * C64[k2] - s1 * S64[k2];            // cos(2 pi k / 1024)
-                const float s = s1 * C64[k2] + c1 * S64[k2];
-                const float zr = re[own], zi = im[own];
-                const float ar = zr + pr, ai = zi - pi;                 // Z[k] + conj Z[512-k]
-                const float br = zr - pr, bi = zi + pi;                 // Z[k] - conj Z[512-k]
-                const float t1 = c * bi - s * br;
-                const float t2 = c * br + s * bi;
-                const float xr = ar + t1, xi = ai - t2;                 // 2 X[k]
-                const float yr = ar - t1, yi = ai + t2;                 // 2 conj-ish X[512-k] (same magnitude)
-                Pown[(k1 + 16 * k2) * kPStride] = 0.25f * (xr * xr + xi * xi);
+                float2 p = make_float2(__shfl_sync(kFull, v[src_other].x, partner),
+                                       __shfl_sync(kFull, v[src_other].y, partner));
+                if (k1 == 0) p = v[src_self];
+                // split twiddle (cos, sin)(2 pi k / 1024) = (c1 + i s1) * (C + i S), k = k1 + 16 k2
+                const float2 cs = c_mul_tw(make_float2(c1, s1), C64[k2], S64[k2]);
+                const float2 pw = rfft_split_power_pair(v[own], p, cs.x, cs.y);
+                Pown[(k1 + 16 * k2) * kPStride] = pw.x;
                 // mirror bin index: 512 - k = k1m + 16 (31 - k2) for k1 != 0, 16 (32 - k2) for k1 == 0
                 const int km = (k1 == 0) ? 16 * (32 - k2) : (k1m + 16 * (31 - k2));
-                if (!(k1 == 0 && k2 == 0)) Pmir[km * kPStride] = 0.25f * (yr * yr + yi * yi);
+                if (!(k1 == 0 && k2 == 0)) Pmir[km * kPStride] = pw.y;
             }
             if (k1 == 0) {
                 // k = 0 was written above (X[0] = Re Z[0] + Im Z[0]); Nyquist and the self-paired k = 256
-                const float v = re[0] - im[0];                          // X[512] = Re Z[0] - Im Z[0]
-                Pown[512 * kPStride] = v * v;
-                const int own = BitRev<32>::of(16);                     // Z[256]: its own mirror
-                const float zr = re[own], zi = im[own];
-                // A = (2 zr, 0), B = (0, 2 zi), (c, s) = (cos, sin)(pi/2) = (0, 1):  X[256] = (zr, -zi)
-                Pown[256 * kPStride] = zr * zr + zi * zi;
+                const float d = v[0].x - v[0].y;                        // X[512] = Re Z[0] - Im Z[0]
+                Pown[512 * kPStride] = d * d;
+                const float2 zq = v[BitRev<32>::of(16)];                // Z[256]: its own mirror, X[256] = conj Z[256]
+                Pown[256 * kPStride] = zq.x * zq.x + zq.y * zq.y;
             }
         }
         __syncthreads();
