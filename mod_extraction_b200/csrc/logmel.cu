@@ -53,6 +53,13 @@ __device__ __forceinline__ int reflect_index(int i, int T) {
     return max(0, min(i, T - 1));      // frames past the end of a short clip are computed but never stored
 }
 
+// log(x) for x >= eps > 0 (never denormal after the clip): one MUFU.LG2 and one multiply, <= 3 ulp
+__device__ __forceinline__ float fast_log(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.69314718055994530942f;
+}
+
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
 }
@@ -171,7 +178,9 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
             // the two 16-byte halves of a power row are swapped on every other group of 4 rows so that
             // rows r and r+4 (same banks) are read / written through different banks
             float* Pown = P + ((lf + f) ^ (((k1 >> 2) & 1) << 2));
-            float* Pmir = P + ((lf + f) ^ (((k1m >> 2) & 1) << 2));
+            // mirror bins: 512 - k = k1m + 16 (31 - k2) for k1 != 0 and 16 (32 - k2) for k1 == 0, i.e. one base
+            // pointer minus k2 * 16 rows in both cases
+            float* Pmir = P + ((lf + f) ^ (((k1m >> 2) & 1) << 2)) + ((k1 == 0) ? 512 : (k1m + 496)) * kPStride;
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) {
                 const int own = BitRev<32>::of(k2);
@@ -184,9 +193,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
                 const float2 cs = c_mul_tw(make_float2(c1, s1), C64[k2], S64[k2]);
                 const float2 pw = rfft_split_power_pair(v[own], p, cs.x, cs.y);
                 Pown[(k1 + 16 * k2) * kPStride] = pw.x;
-                // mirror bin index: 512 - k = k1m + 16 (31 - k2) for k1 != 0, 16 (32 - k2) for k1 == 0
-                const int km = (k1 == 0) ? 16 * (32 - k2) : (k1m + 16 * (31 - k2));
-                if (!(k1 == 0 && k2 == 0)) Pmir[km * kPStride] = pw.y;
+                if (!(k1 == 0 && k2 == 0)) Pmir[-k2 * 16 * kPStride] = pw.y;
             }
             if (k1 == 0) {
                 // k = 0 was written above (X[0] = Re Z[0] + Im Z[0]); Nyquist and the self-paired k = 256
@@ -215,13 +222,15 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
 #pragma unroll
                     for (int t = 0; t < kFB; ++t) acc[t] = 0.0f;
                     const int r0 = (int)mstart[m];
+                    const char* Pbytes = reinterpret_cast<const char*>(P);
 #pragma unroll 2
                     for (int j = 0; j < cnt; ++j) {
                         const float wj = w[j];
-                        const int r = r0 + j;
-                        const int sw = (r >> 2) & 1;
-                        const float4 p0 = *reinterpret_cast<const float4*>(P + r * kPStride + 4 * sw);
-                        const float4 p1 = *reinterpret_cast<const float4*>(P + r * kPStride + 4 - 4 * sw);
+                        // row r starts at byte 32 r; its two 16-byte halves are swapped when bit 2 of r is set
+                        const unsigned lin = (unsigned)(r0 + j) * 32u;
+                        const unsigned lo16 = lin ^ ((lin >> 3) & 16u);
+                        const float4 p0 = *reinterpret_cast<const float4*>(Pbytes + lo16);
+                        const float4 p1 = *reinterpret_cast<const float4*>(Pbytes + (lo16 ^ 16u));
                         acc[0] = fmaf(wj, p0.x, acc[0]); acc[1] = fmaf(wj, p0.y, acc[1]);
                         acc[2] = fmaf(wj, p0.z, acc[2]); acc[3] = fmaf(wj, p0.w, acc[3]);
                         acc[4] = fmaf(wj, p1.x, acc[4]); acc[5] = fmaf(wj, p1.y, acc[5]);
@@ -231,10 +240,10 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
                     // stores below are 32-byte segments instead of 4-byte scatters
                     float4 o0, o1;
                     if (a.apply_log) {
-                        o0 = make_float4(__logf(fmaxf(acc[0], a.eps)), __logf(fmaxf(acc[1], a.eps)),
-                                         __logf(fmaxf(acc[2], a.eps)), __logf(fmaxf(acc[3], a.eps)));
-                        o1 = make_float4(__logf(fmaxf(acc[4], a.eps)), __logf(fmaxf(acc[5], a.eps)),
-                                         __logf(fmaxf(acc[6], a.eps)), __logf(fmaxf(acc[7], a.eps)));
+                        o0 = make_float4(fast_log(fmaxf(acc[0], a.eps)), fast_log(fmaxf(acc[1], a.eps)),
+                                         fast_log(fmaxf(acc[2], a.eps)), fast_log(fmaxf(acc[3], a.eps)));
+                        o1 = make_float4(fast_log(fmaxf(acc[4], a.eps)), fast_log(fmaxf(acc[5], a.eps)),
+                                         fast_log(fmaxf(acc[6], a.eps)), fast_log(fmaxf(acc[7], a.eps)));
                     } else {
                         o0 = make_float4(acc[0], acc[1], acc[2], acc[3]);
                         o1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -246,13 +255,17 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
             __syncthreads();
             // 8 consecutive lanes write the 8 frames of one band: one 32-byte segment per band row
             const int live = min(kFB, a.n_frames - t0);
-            for (int idx = tid; idx < a.n_mels * kFB; idx += kThreads) {
-                const int m = idx >> 3, t = idx & (kFB - 1);
-#ifdef MODFX_EXP_NO_STORE
-                if (t < live && E[idx] == 12345.678f) orow[(int64_t)m * a.n_frames + t0 + t] = E[idx];
-#else
-                if (t < live) orow[(int64_t)m * a.n_frames + t0 + t] = E[idx];
-#endif
+            const int t = tid & (kFB - 1);
+            if (t < live) {
+                const float* ep = E + tid;
+                float* op = orow + (int64_t)(tid >> 3) * a.n_frames + t0 + t;
+                const int64_t ostep = (int64_t)(kThreads / kFB) * a.n_frames;
+#pragma unroll 4
+                for (int m = tid >> 3; m < a.n_mels; m += kThreads / kFB) {
+                    *op = *ep;
+                    op += ostep;
+                    ep += kThreads;
+                }
             }
         }
 #endif
