@@ -113,18 +113,26 @@ __global__ void __launch_bounds__(kK0Threads) phaser_ctl_kernel(const PhaserArgs
     }
 }
 
-// One sample of the cascade.  With c = 2G-1 the TPT all-pass (v = G(in-s); y = v+s; s' = y+v;
-// out = 2y-in) is out = s + c*(in-s), s' = in + c*(in-s): three instructions per stage.
-__device__ __forceinline__ float cascade_step(float in, float (&s)[kStagesAP], float c) {
+// One sample of the cascade.  With c = 2G-1 the TPT all-pass (v = G(in-s); y = v+s; s' = y+v; out = 2y-in)
+// is out = c*in + (1-c)*s, s' = (1+c)*in - c*s.  Carrying w = (1-c)*s instead of s turns every stage into
+// the transposed direct form II of a first-order all-pass -- two dependent FMAs:  out = c*in + w,
+// w' = in - c*out  -- at the price of rescaling w by (1-c_new)/(1-c_old) when the coefficient moves (every
+// 4th sample).  All kernels keep the states in this form, scaled for the coefficient of the last sample done.
+__device__ __forceinline__ float cascade_step(float in, float (&w)[kStagesAP], float c) {
     float v = in;
 #pragma unroll
     for (int k = 0; k < kStagesAP; ++k) {
-        const float d = v - s[k];
-        const float o = fmaf(c, d, s[k]);
-        s[k] = fmaf(c, d, v);
-        v = o;
+        const float y = fmaf(c, v, w[k]);
+        w[k] = fmaf(-c, y, v);
+        v = y;
     }
     return v;
+}
+
+__device__ __forceinline__ void cascade_retune(float (&w)[kStagesAP], float c_old, float c_new) {
+    const float r = __fdividef(1.0f - c_new, 1.0f - c_old);     // 1 - c = 2 (1 - G) in (0.06, 2]: well conditioned
+#pragma unroll
+    for (int k = 0; k < kStagesAP; ++k) w[k] *= r;
 }
 
 // ---- K1: per-chunk affine map ----------------------------------------------------------------
@@ -132,13 +140,17 @@ __device__ __forceinline__ float cascade_step(float in, float (&s)[kStagesAP], f
 // driven by x) for 32 consecutive chunks, lane = chunk.  The run index is warp-uniform, so the
 // homogeneous warps never touch the audio.
 template <bool DRIVEN>
-__device__ __forceinline__ void map_run(const float (*xs)[kChunk + 1], const float (*cs)[kCtl + 1], int ch, int len,
-                                        float fbk, float (&s)[kStagesAP], float& out_prev, int j_begin) {
-    // out_prev holds the previous cascade output; lastOutput = out_prev * feedback
-    if (len == kChunk && j_begin == 0) {       // full chunk: no guards, one coefficient per 4 samples
+__device__ __forceinline__ void map_run(const float (*xs)[kChunk + 1], const float (*cs)[kCtl + 2], int ch, int len,
+                                        float fbk, float (&s)[kStagesAP], float& out_prev, int j_begin, float c_cur) {
+    // j_begin is 0, or kUpd when the caller has already done the first control group by hand
+    // out_prev holds the previous cascade output; lastOutput = out_prev * feedback.
+    // cs[ch][0] is the coefficient of the sample before the chunk, cs[ch][1 + g] that of control group g.
+    if (len == kChunk) {                       // full chunk: no guards, one coefficient per 4 samples
 #pragma unroll 2
-        for (int g = 0; g < kCtl; ++g) {
-            const float c = cs[ch][g];
+        for (int g = j_begin / kUpd; g < kCtl; ++g) {
+            const float c = cs[ch][1 + g];
+            cascade_retune(s, c_cur, c);
+            c_cur = c;
 #pragma unroll
             for (int q = 0; q < kUpd; ++q) {
                 const float u = DRIVEN ? fmaf(-fbk, out_prev, xs[ch][g * kUpd + q]) : -fbk * out_prev;
@@ -147,7 +159,11 @@ __device__ __forceinline__ void map_run(const float (*xs)[kChunk + 1], const flo
         }
     } else {
         for (int j = j_begin; j < len; ++j) {
-            const float c = cs[ch][j >> 2];
+            const float c = cs[ch][1 + (j >> 2)];
+            if (c != c_cur) {
+                cascade_retune(s, c_cur, c);
+                c_cur = c;
+            }
             const float u = DRIVEN ? fmaf(-fbk, out_prev, xs[ch][j]) : -fbk * out_prev;
             out_prev = cascade_step(u, s, c);
         }
@@ -156,7 +172,7 @@ __device__ __forceinline__ void map_run(const float (*xs)[kChunk + 1], const flo
 
 __global__ void __launch_bounds__(256) phaser_map_kernel(const PhaserArgs a, int n_super) {
     __shared__ float xs[32][kChunk + 1];
-    __shared__ float cs[32][kCtl + 1];
+    __shared__ float cs[32][kCtl + 2];
     const int item = blockIdx.x / n_super, sc = blockIdx.x - item * n_super;
     const int b = example_of(a, item);
     const int tid = threadIdx.x;
@@ -167,9 +183,10 @@ __global__ void __launch_bounds__(256) phaser_map_kernel(const PhaserArgs a, int
         xs[i / kChunk][i % kChunk] = (n < a.N) ? xr[n] : 0.0f;
     }
     const float* cr = a.C + (int64_t)item * a.n_ctl;
-    for (int i = tid; i < 32 * kCtl; i += 256) {
-        const int j = n_base / kUpd + i;
-        cs[i / kCtl][i % kCtl] = (j < a.n_ctl) ? cr[j] : 0.0f;
+    for (int i = tid; i < 32 * (kCtl + 1); i += 256) {
+        const int row = i / (kCtl + 1), col = i % (kCtl + 1);          // col 0 = coefficient before the chunk
+        const int j = n_base / kUpd + row * kCtl + col - 1;
+        cs[row][col] = cr[max(0, min(j, a.n_ctl - 1))];
     }
     __syncthreads();
     const int run = tid >> 5, ch = tid & 31;
@@ -183,13 +200,19 @@ __global__ void __launch_bounds__(256) phaser_map_kernel(const PhaserArgs a, int
     // state 6 is lastOutput = out_prev * feedback: a unit lastOutput is out_prev = 1 / feedback.  To stay
     // finite for feedback = 0 the unit run carries `last` itself through the first sample.
     float out_prev = 0.0f;
+    const float c_prev = cs[ch][0];
     if (run == 7) {
-        map_run<true>(xs, cs, ch, len, fbk, s, out_prev, 0);
+        map_run<true>(xs, cs, ch, len, fbk, s, out_prev, 0, c_prev);
     } else if (run == 6) {
-        out_prev = cascade_step(-1.0f, s, cs[ch][0]);       // first sample by hand: u = -lastOutput = -1
-        map_run<false>(xs, cs, ch, len, fbk, s, out_prev, 1);
+        // unit lastOutput: first control group by hand (u = -1 for the first sample); the all-pass states are
+        // zero before it, so there is nothing to retune
+        const float c0 = cs[ch][1];
+        out_prev = cascade_step(-1.0f, s, c0);
+        const int n0 = min(kUpd, len);
+        for (int q = 1; q < n0; ++q) out_prev = cascade_step(-fbk * out_prev, s, c0);
+        map_run<false>(xs, cs, ch, len, fbk, s, out_prev, kUpd, c0);
     } else {
-        map_run<false>(xs, cs, ch, len, fbk, s, out_prev, 0);
+        map_run<false>(xs, cs, ch, len, fbk, s, out_prev, 0, c_prev);
     }
     float* m = a.Mw + ((int64_t)item * a.n_chunks + chunk) * kMapFloats + run * kState;
 #pragma unroll
@@ -283,6 +306,7 @@ __global__ void __launch_bounds__(32 * kRunWarps) phaser_run_kernel(const Phaser
         for (int k = 0; k < kStagesAP; ++k) s[k] = 0.0f;
     }
     const int len = live ? min(kChunk, a.N - chunk * kChunk) : 0;
+    float c_cur = cr[max(0, min(chunk * kCtl - 1, a.n_ctl - 1))];      // coefficient of the sample before the chunk
     for (int q0 = 0; q0 < kChunk; q0 += 32) {                          // 4 sub-tiles of 32 samples
         __syncwarp();
 #pragma unroll 4
@@ -295,6 +319,8 @@ __global__ void __launch_bounds__(32 * kRunWarps) phaser_run_kernel(const Phaser
 #pragma unroll 2
             for (int g = 0; g < 8; ++g) {
                 const float c = ct[lane][(q0 >> 2) + g];
+                cascade_retune(s, c_cur, c);
+                c_cur = c;
 #pragma unroll
                 for (int q = 0; q < kUpd; ++q) {
                     const float in = t[lane][g * kUpd + q];
@@ -306,6 +332,10 @@ __global__ void __launch_bounds__(32 * kRunWarps) phaser_run_kernel(const Phaser
         } else {
             for (int q = 0; q0 + q < len && q < 32; ++q) {
                 const float c = ct[lane][(q0 + q) >> 2];
+                if (c != c_cur) {
+                    cascade_retune(s, c_cur, c);
+                    c_cur = c;
+                }
                 const float in = t[lane][q];
                 const float out = cascade_step(in - last, s, c);
                 last = out * fbk;
