@@ -92,14 +92,14 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogMelArgs a)
         sincospif(-(float)(n2 * k1) / 256.0f, &s, &c);
         tw1[i] = make_float2(c, s);
     }
-    // compact copy of the banded mel table (<= 14 taps per band for the reference configuration)
-    if (tid == 0) {
+    // compact copy of the banded mel table (<= 14 taps per band for the reference configuration):
+    // counts -> exclusive prefix (every thread sums the counts below its band from shared memory)
+    for (int m = tid; m < a.n_mels; m += kThreads) mstart[m] = (unsigned short)min(a.fb_count[m], 65535);
+    __syncthreads();
+    for (int m = tid; m <= a.n_mels; m += kThreads) {
         int off = 0;
-        for (int m = 0; m < a.n_mels; ++m) {
-            moff[m] = (unsigned short)off;
-            off += min(a.fb_count[m], a.fb_taps - off);
-        }
-        moff[a.n_mels] = (unsigned short)off;
+        for (int i = 0; i < m; ++i) off += mstart[i];
+        moff[m] = (unsigned short)min(off, a.fb_taps);
     }
     __syncthreads();
     for (int m = tid; m < a.n_mels; m += kThreads) {
@@ -307,6 +307,8 @@ extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T
     a.row_index = row_index;
     const int iters = (a.n_frames + kFB - 1) / kFB;
     // enough CTAs to fill the chip twice over even for a handful of rows
+    // One CTA per row unless there are too few rows to fill the chip a few times over (every CTA pays
+    // the table set-up and its first span is staged synchronously; finer chunking measured slower).
     int chunks = 1;
     const int64_t want = 4ll * num_sms();
     if (R < want) chunks = (int)((want + R - 1) / R);
