@@ -295,7 +295,7 @@ def main():
         "chorus": (lambda: _ops.flanger_chorus(dry, ModSource.control_rate(mod_lo), Rs.ch[0], Rs.ch[1], *fc_args,
                                                example_index=i_ch, out=wet), i_ch.numel() * N * 8, 1),
         "phaser": (lambda: _ops.phaser(dry2, float(SR), *ph_args, example_index=i_ph, out=wet2),
-                   i_ph.numel() * N * 8, 5),
+                   i_ph.numel() * N * 8, 4),
         "logmel": (lambda: Rs.front.forward_rows(dry2, N, B, logmel.view(-1), N, 2 * nm, None),
                    B * (N * 4 + nm * 4), 1),
     }
@@ -313,20 +313,30 @@ def main():
         kernels[name] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9, "launches": n_launch}
     step()                                                      # leave wet / log-mel consistent again
 
-    peaks = {}
+    peaks, traffic_tab = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    units = {"logmel": ("bytes_per_row", B), "flanger": ("bytes_per_example", i_fl.numel()),
+             "chorus": ("bytes_per_example", i_ch.numel()), "phaser": ("bytes_per_example", i_ph.numel())}
+    for name, (key, n_units) in units.items():
+        t = traffic_tab.get(name, {}).get(key)
+        kernels[name]["dram_traffic_bytes"] = None if t is None else t * n_units
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     dom = max(kernels, key=lambda k: kernels[k]["ms"] * (2 if k == "logmel" else 1))
     roofline = {"bound": "hbm", "kernel": {"logmel": "logmel_kernel (one launch over B dry rows; the wet half is a second identical launch)",
                                            "flanger": "fc_kernel<control-rate> (flanger group)",
                                            "chorus": "fc_kernel<control-rate> (chorus group)",
-                                           "phaser": "phaser_{phase,coef,map,scan,run}_kernel (5 launches)"}[dom],
+                                           "phaser": "phaser_{ctl,map,scan,run}_kernel (4 launches)"}[dom],
                 "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["gbs"] / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": kernels[dom].get("dram_traffic_bytes"), "peak_source": peak_src,
+                "traffic_source": "ncu dram__bytes_read+write per unit of work (profiles/traffic.json), scaled to this launch",
                 "how": "algorithmic bytes of the launch / median CUDA-event duration, launches serialised on one stream "
                        "after the timed region (inside the timed region the four streams overlap)",
                 "pipeline": {"achieved": world * B * BYTES_PER_EXAMPLE / (ms_per_step * 1e-3) / 1e9 / world,
@@ -404,7 +414,7 @@ def main():
                        "host RNG before the timed region; x100 upsample fused in the effect kernel",
                        "l2": "inputs (1.4 GB dry + 1.4 GB wet + 2.9 GB log-mel per step) far exceed the 126 MB L2",
                        "parallelism": f"batch-sharded x{world}, no collective while rendering"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * 11,      # per step: flanger 1 + chorus 1 + phaser 5 + log-mel 4
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * 10,      # per step: flanger 1 + chorus 1 + phaser 4 + log-mel 4
             "roofline": roofline,
             "cpu_baseline": cpu_baseline, "lfo_generation_s": lfo_gen_s, "metrics_gather_ms": gather_ms,
             "wet_abs_mean": checksum,
