@@ -11,7 +11,8 @@
 //       coefficient c = 2G-1 for every 4th sample;
 //   K1  for every chunk of 128 samples, 8 independent runs give the chunk's state-transition matrix
 //       (7 homogeneous runs from the unit states) and its zero-state response (1 run with the audio);
-//   K2  a short serial pass per example chains the 7x7 maps to get the true state at every chunk start;
+//   K2  the 7x7 maps are chained to get the true state at every chunk start: groups of 32 maps are composed
+//       in parallel, the group maps chained serially, and every group re-chained from its initial state;
 //   K3  every chunk is re-run from its true initial state and writes the mixed, clipped output.
 // K1 and K3 stage audio through shared memory so global traffic stays coalesced.
 #include "common.cuh"
@@ -222,40 +223,88 @@ __global__ void __launch_bounds__(256) phaser_map_kernel(const PhaserArgs a, int
 
 // ---- K2: chain the maps: state at the start of every chunk --------------------------------------
 // 8 lanes per example; lane i < 7 owns state component i.
-__global__ void __launch_bounds__(256) phaser_scan_kernel(const PhaserArgs a) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int item = gid >> 3, i = gid & 7;
-    const bool live = item < a.n_items;
-    const int it = live ? item : 0;
-    const float* m = a.Mw + (int64_t)it * a.n_chunks * kMapFloats;
-    float* S = a.S + (int64_t)it * a.n_chunks * kSFloats;
+// The chain of n_chunks affine maps per example is resolved in three short passes instead of one long
+// one (689 dependent steps for 2 s, 20 672 for 60 s): (a) groups of 32 consecutive chunk maps are
+// composed into one map each, all groups in parallel; (b) the group maps are chained serially (22 steps
+// for 2 s); (c) every group re-chains its 32 chunk maps from its now known initial state.
+constexpr int kGroup = 32;
+constexpr int kSerialChainMax = 4096;     // up to this many maps per example a single serial chain is used (measured faster)
+
+// (a) compose the maps of one group: 8 lanes per group, lane r carries column r of [Phi | z]
+__global__ void __launch_bounds__(256) phaser_compose_kernel(const PhaserArgs a, int n_groups, float* __restrict__ GM) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t team = gid >> 3;
+    const int r = (int)(gid & 7);
+    if (team >= (int64_t)a.n_items * n_groups) return;
+    const int item = (int)(team / n_groups), g = (int)(team - (int64_t)item * n_groups);
+    const int c0 = g * kGroup, c1 = min(c0 + kGroup, a.n_chunks);
+    const float* m = a.Mw + ((int64_t)item * a.n_chunks + c0) * kMapFloats;
+    float col[kState];
+#pragma unroll
+    for (int i = 0; i < kState; ++i) col[i] = (i == r) ? 1.0f : 0.0f;      // r == 7: the z column starts at 0
+    for (int c = c0; c < c1; ++c, m += kMapFloats) {
+        float nxt[kState];
+#pragma unroll
+        for (int i = 0; i < kState; ++i) nxt[i] = (r == 7) ? __ldg(m + 7 * kState + i) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < kState; ++k) {
+#pragma unroll
+            for (int i = 0; i < kState; ++i) nxt[i] = fmaf(__ldg(m + k * kState + i), col[k], nxt[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < kState; ++i) col[i] = nxt[i];
+    }
+    float* o = GM + team * kMapFloats + r * kState;
+#pragma unroll
+    for (int i = 0; i < kState; ++i) o[i] = col[i];
+}
+
+// (b), (c) chain maps [seg * seg_len, (seg + 1) * seg_len) of every example from an initial state
+// (zero when init == nullptr), writing the state at the start of every map.  8 lanes per segment;
+// lane i < 7 owns state component i.
+__global__ void __launch_bounds__(256) phaser_chain_kernel(const float* __restrict__ maps, int n_maps, int seg_len,
+                                                           int n_items, const float* __restrict__ init,
+                                                           float* __restrict__ out) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)(gid & 7);
+    const int n_seg = (n_maps + seg_len - 1) / seg_len;
+    int64_t team = gid >> 3;
+    const bool live = team < (int64_t)n_items * n_seg;
+    if (!live) team = 0;
+    const int item = (int)(team / n_seg), seg = (int)(team - (int64_t)item * n_seg);
+    const int c0 = seg * seg_len, c1 = min(c0 + seg_len, n_maps);
+    const float* m = maps + ((int64_t)item * n_maps + c0) * kMapFloats;
+    float* S = out + ((int64_t)item * n_maps + c0) * kSFloats;
     const int ii = (i < kState) ? i : 0;
-    constexpr int kAhead = 4;                  // chunks of map coefficients in flight (they do not depend on s)
+    const int n = c1 - c0;
+    constexpr int kAhead = 4;                  // maps in flight (their coefficients do not depend on the state)
     float buf[kAhead][8];
 #pragma unroll
     for (int d = 0; d < kAhead; ++d) {
-        const float* mc = m + (int64_t)min(d, a.n_chunks - 1) * kMapFloats;
+        const float* mc = m + (int64_t)min(d, n - 1) * kMapFloats;
 #pragma unroll
         for (int r = 0; r < 8; ++r) buf[d][r] = mc[r * kState + ii];
     }
-    float s = 0.0f;
-    for (int c0 = 0; c0 < a.n_chunks; c0 += kAhead) {
+    float s = (init && i < kState) ? init[((int64_t)item * n_seg + seg) * kSFloats + i] : 0.0f;
+    // every team of the warp runs the same number of steps (the shuffles below need all 32 lanes);
+    // steps past the end of a short last segment are computed and discarded
+    for (int b0 = 0; b0 < seg_len; b0 += kAhead) {
 #pragma unroll
         for (int d = 0; d < kAhead; ++d) {
-            const int cidx = c0 + d;
+            const int cidx = b0 + d;
             float cur[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) cur[r] = buf[d][r];
-            {   // refill this slot with chunk cidx + kAhead
-                const float* mc = m + (int64_t)min(cidx + kAhead, a.n_chunks - 1) * kMapFloats;
+            {   // refill this slot with map cidx + kAhead
+                const float* mc = m + (int64_t)min(cidx + kAhead, n - 1) * kMapFloats;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) buf[d][r] = mc[r * kState + ii];
             }
-            if (cidx < a.n_chunks) {
-                if (live) S[cidx * kSFloats + i] = s;
-                float acc = cur[7];                                    // zero-state response
+            float acc = cur[7];                                        // zero-state response
 #pragma unroll
-                for (int r = 0; r < kState; ++r) acc = fmaf(cur[r], __shfl_sync(kFull, s, r, 8), acc);
+            for (int r = 0; r < kState; ++r) acc = fmaf(cur[r], __shfl_sync(kFull, s, r, 8), acc);
+            if (cidx < n) {
+                if (live) S[cidx * kSFloats + i] = s;
                 s = (i < kState) ? acc : 0.0f;
             }
         }
@@ -362,7 +411,9 @@ extern "C" int64_t modfx_phaser_workspace_bytes(int32_t B, int64_t N) {
     if (B <= 0 || N <= 0) return 0;
     const int64_t n_ctl = (N + kUpd - 1) / kUpd, n_chunks = (N + kChunk - 1) / kChunk;
     return align_up((int64_t)B * n_ctl * 4, 256) + align_up((int64_t)B * n_chunks * kMapFloats * 4, 256) +
-           align_up((int64_t)B * n_chunks * kSFloats * 4, 256);
+           align_up((int64_t)B * n_chunks * kSFloats * 4, 256) +
+           align_up((int64_t)B * ((n_chunks + 31) / 32) * kMapFloats * 4, 256) +
+           align_up((int64_t)B * ((n_chunks + 31) / 32) * kSFloats * 4, 256);
 }
 
 extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, const float* rate_hz,
@@ -389,6 +440,7 @@ extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, 
     a.Mw = reinterpret_cast<float*>(w);
     w += align_up((int64_t)a.n_items * a.n_chunks * kMapFloats * 4, 256);
     a.S = reinterpret_cast<float*>(w);
+    w += align_up((int64_t)a.n_items * a.n_chunks * kSFloats * 4, 256);
     cudaStream_t s = as_stream(stream);
 
     const int n_blocks = (int)((N + block - 1) / block);
@@ -400,7 +452,22 @@ extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, 
         const int n_super = (a.n_chunks + 31) / 32;
         phaser_map_kernel<<<(unsigned)((int64_t)a.n_items * n_super), 256, 0, s>>>(a, n_super);
     }
-    phaser_scan_kernel<<<(a.n_items * 8 + 255) / 256, 256, 0, s>>>(a);
+    if (a.n_chunks <= kSerialChainMax) {
+        // short clips (689 maps for 2 s): one serial chain per example is the cheapest
+        phaser_chain_kernel<<<(unsigned)(((int64_t)a.n_items * 8 + 255) / 256), 256, 0, s>>>(a.Mw, a.n_chunks, a.n_chunks,
+                                                                                          a.n_items, nullptr, a.S);
+    } else {
+        // long clips (20 672 maps for 60 s): compose groups in parallel, chain the groups, re-chain inside groups
+        const int n_groups = (a.n_chunks + kGroup - 1) / kGroup;
+        float* GM = reinterpret_cast<float*>(w);
+        w += align_up((int64_t)a.n_items * n_groups * kMapFloats * 4, 256);
+        float* GS = reinterpret_cast<float*>(w);
+        const int64_t teams = (int64_t)a.n_items * n_groups;
+        phaser_compose_kernel<<<(unsigned)((teams * 8 + 255) / 256), 256, 0, s>>>(a, n_groups, GM);
+        phaser_chain_kernel<<<(unsigned)(((int64_t)a.n_items * 8 + 255) / 256), 256, 0, s>>>(GM, n_groups, n_groups, a.n_items,
+                                                                                          nullptr, GS);
+        phaser_chain_kernel<<<(unsigned)((teams * 8 + 255) / 256), 256, 0, s>>>(a.Mw, a.n_chunks, kGroup, a.n_items, GS, a.S);
+    }
     {
         const int64_t warps = (int64_t)a.n_items * ((a.n_chunks + 31) / 32);
         phaser_run_kernel<<<(unsigned)((warps + kRunWarps - 1) / kRunWarps), 32 * kRunWarps, 0, s>>>(a);
