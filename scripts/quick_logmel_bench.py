@@ -4,7 +4,7 @@ import numpy as np, torch
 from mod_extraction_b200.models import LogMelSpectrogram
 dev = "cuda:0"
 front = LogMelSpectrogram().to(dev)
-for B in (64, 512, 4096):
+for B in (64, 683, 2048, 4096):
     x = (torch.rand((B, 2, 88200), device=dev) - 0.5)
     out = torch.empty((B, 2, 256, 345), device=dev)
     for _ in range(3): front(x, out=out)
