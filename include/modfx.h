@@ -141,6 +141,27 @@ int modfx_stretch_sections_f32(const float* in, float* out, int32_t B, int64_t n
                                const int32_t* out_start, void* stream);
 
 /*
+ * Post-processing of extracted LFOs (eval path), mod_extraction/modulations.py:259-362.  Rows are
+ * independent (n frames each, 345 for 2 s of audio); all float32 arithmetic in the reference's order.
+ *   modfx_smoothen_f32         replaces smoothen, modulations.py:358-362: out (rows, n - window + 1) =
+ *                              moving average of in (rows, n) over `window` frames, no padding.
+ *   modfx_stretch_corners_f32  replaces find_corners + _stretch_corners of stretch_corners,
+ *                              modulations.py:259-307, applied to an already smoothed signal: every
+ *                              stretch between neighbouring corners is rescaled so that top corners reach
+ *                              1.0 and bottom corners 0.0; rows with more than max_n_corners corners
+ *                              are copied unchanged.  in and out must not alias.
+ *   modfx_check_mod_sig_f32    replaces check_mod_sig / find_valid_mod_sig_indices, modulations.py:311-355:
+ *                              valid[r] = 1 when row r has min..max top and bottom corners and neighbouring
+ *                              corners of a kind are at least min_frames apart.
+ */
+int modfx_smoothen_f32(const float* in, float* out, int64_t rows, int64_t n, int32_t window, void* stream);
+int modfx_stretch_corners_f32(const float* in, float* out, int64_t rows, int64_t n, int32_t max_n_corners,
+                              void* stream);
+int modfx_check_mod_sig_f32(const float* in, uint8_t* valid, int64_t rows, int64_t n, int32_t min_top,
+                            int32_t max_top, int32_t min_bottom, int32_t max_bottom, int32_t min_frames,
+                            void* stream);
+
+/*
  * Replaces Spectral2DCNN.spectrogram + clip + log, mod_extraction/models.py:170-175,199,207-208
  * (torchaudio MelSpectrogram n_fft=1024, hop 256, center/reflect, periodic Hann, power 2).
  *   x         (R, T) rows = batch*channels

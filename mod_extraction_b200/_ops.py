@@ -225,6 +225,43 @@ def find_corners(mod_sig: Tensor):
     return top, bottom
 
 
+def smoothen(x: Tensor, window: int) -> Tensor:
+    """(rows, n) CUDA float32 -> (rows, n - window + 1) moving average (modulations.py:358-362)."""
+    _require_cuda(x, "x")
+    assert x.ndim == 2 and 1 <= window <= x.size(1)
+    m = x.contiguous()
+    out = torch.empty((m.size(0), m.size(1) - window + 1), device=m.device, dtype=torch.float32)
+    with torch.cuda.device(m.device):
+        _lib.check(_lib.lib().modfx_smoothen_f32(_ptr(m), _ptr(out), m.size(0), m.size(1), int(window), _stream()))
+    return out
+
+
+def stretch_corners(x: Tensor, max_n_corners: int) -> Tensor:
+    """find_corners + _stretch_corners on an already smoothed (rows, n) CUDA float32 signal
+    (modulations.py:259-307)."""
+    _require_cuda(x, "x")
+    assert x.ndim == 2
+    m = x.contiguous()
+    out = torch.empty_like(m)
+    with torch.cuda.device(m.device):
+        _lib.check(_lib.lib().modfx_stretch_corners_f32(_ptr(m), _ptr(out), m.size(0), m.size(1), int(max_n_corners),
+                                                        _stream()))
+    return out
+
+
+def check_mod_sig(x: Tensor, min_top: int, max_top: int, min_bottom: int, max_bottom: int, min_frames: int) -> Tensor:
+    """(rows, n) CUDA float32 -> (rows,) uint8 validity flags (modulations.py:311-345)."""
+    _require_cuda(x, "x")
+    assert x.ndim == 2
+    m = x.contiguous()
+    valid = torch.empty((m.size(0),), device=m.device, dtype=torch.uint8)
+    with torch.cuda.device(m.device):
+        _lib.check(_lib.lib().modfx_check_mod_sig_f32(_ptr(m), _ptr(valid), m.size(0), m.size(1), int(min_top),
+                                                      int(max_top), int(min_bottom), int(max_bottom), int(min_frames),
+                                                      _stream()))
+    return valid
+
+
 def _i32(values, device) -> Tensor:
     return torch.tensor(values, dtype=torch.int32).to(device, non_blocking=True)
 

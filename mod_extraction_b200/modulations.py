@@ -17,7 +17,8 @@ from ._lib import SHAPE_ID, SHAPES
 
 __all__ = ["SHAPES", "SHAPE_ID", "make_mod_signal", "make_mod_signal_batch", "make_rand_mod_signal",
            "lfo_kernel_params", "find_corners", "make_quasi_periodic", "make_quasi_periodic_batch",
-           "make_combined_mod_sig", "make_combined_mod_sig_batch"]
+           "make_combined_mod_sig", "make_combined_mod_sig_batch", "smoothen", "stretch_corners",
+           "find_valid_mod_sig_indices", "mod_sig_to_corners"]
 
 
 def _device() -> tr.device:
@@ -234,3 +235,51 @@ def make_combined_mod_sig(n_samples: int,
                           device=None) -> T:
     """modulations.py:191-210."""
     return make_combined_mod_sig_batch(n_samples, sr, [float(freq)], [float(phase)], shapes, device)[0]
+
+
+# --------------------------------------------------------------------------- extracted-LFO post-processing
+# (eval path of the reference: lightning.py:114-127,284-300,325-337)
+
+def _to_dev(x: T) -> Tuple[T, bool]:
+    on_cpu = not x.is_cuda
+    return (x.detach().float().to(_device()) if on_cpu else x.detach().float()), on_cpu
+
+
+def smoothen(x: T, smooth_n_frames: int) -> T:
+    """modulations.py:358-362: moving average over the last dim, (..., n) -> (..., n - smooth_n_frames + 1)."""
+    if smooth_n_frames <= 1:
+        return x
+    xd, on_cpu = _to_dev(x)
+    lead = xd.shape[:-1]
+    out = _ops.smoothen(xd.reshape(-1, xd.size(-1)), smooth_n_frames).reshape(lead + (-1,))
+    return out.cpu() if on_cpu else out
+
+
+def mod_sig_to_corners(mod_sig: T, n_frames: int) -> Tuple[T, T]:
+    """modulations.py:212-215."""
+    assert mod_sig.ndim == 2
+    return find_corners(util.linear_interpolate_last_dim(mod_sig, n_frames, align_corners=True))
+
+
+def stretch_corners(mod_sig: T, max_n_corners: int = 10, smooth_n_frames: int = 32) -> T:
+    """modulations.py:294-307: smooth, find the corners and stretch every row so that its top corners
+    reach 1 and its bottom corners 0; rows with more than ``max_n_corners`` corners are only smoothed.
+    Two launches for the whole batch instead of a python loop over rows and corners."""
+    assert mod_sig.ndim == 2
+    xd, on_cpu = _to_dev(mod_sig)
+    if smooth_n_frames > 1:
+        xd = _ops.smoothen(xd, smooth_n_frames)
+    out = _ops.stretch_corners(xd, max_n_corners)
+    return out.cpu() if on_cpu else out
+
+
+def find_valid_mod_sig_indices(mod_sig: T, min_top_corners: int = 1, max_top_corners: int = 6,
+                               min_bottom_corners: int = 1, max_bottom_corners: int = 6,
+                               min_fraction_between_corners: float = 0.10) -> List[int]:
+    """modulations.py:348-355 with the thresholds of check_mod_sig (:311-345) as keywords."""
+    assert mod_sig.ndim == 2
+    xd, _ = _to_dev(mod_sig)
+    min_n_frames = int(min_fraction_between_corners * xd.size(-1))
+    valid = _ops.check_mod_sig(xd, min_top_corners, max_top_corners, min_bottom_corners, max_bottom_corners,
+                               min_n_frames)
+    return tr.nonzero(valid, as_tuple=True)[0].tolist()

@@ -392,3 +392,104 @@ def phaser(x: np.ndarray, sr: float, rate_hz, depth, centre_frequency_hz, feedba
     y = np.empty_like(x)
     lib().modfx_oracle_phaser(_ptr(x), _ptr(y), B, N, np.float32(sr), *[_ptr(a) for a in args], int(block))
     return y
+
+
+# --------------------------------------------------------------------------- extracted-LFO post-processing (N4)
+
+def smoothen(x: np.ndarray, smooth_n_frames: int) -> np.ndarray:
+    """smoothen, modulations.py:358-362: moving average over `smooth_n_frames` frames, no padding.
+
+    torch's CPU mean over the last dim of the unfold view adds float32 in a fixed order, restated here: four
+    8-lane vector accumulators over blocks of 32 elements, remaining whole 8-vectors into accumulators 0, 1, 2,
+    the four accumulators added left to right, the 8 lanes added left to right, then the scalar tail; finally
+    a true division by the window length.  Bitwise for the windows the reference ships (4, 8, and the default
+    32) and every window that is < 5 or a multiple of 8; within 2e-7 otherwise."""
+    x = _f32(x)
+    w = int(smooth_n_frames)
+    if w <= 1:
+        return x
+    win = np.lib.stride_tricks.sliding_window_view(x, w, axis=-1)          # (..., n_out, w)
+    acc = np.zeros(win.shape[:-1] + (4, 8), dtype=np.float32)
+    i = 0
+    while i + 32 <= w:
+        acc = (acc + win[..., i:i + 32].reshape(win.shape[:-1] + (4, 8))).astype(np.float32)
+        i += 32
+    j = 0
+    while i + 8 <= w:
+        acc[..., j, :] = (acc[..., j, :] + win[..., i:i + 8]).astype(np.float32)
+        i += 8
+        j += 1
+    v = acc[..., 0, :]
+    for j in range(1, 4):
+        v = (v + acc[..., j, :]).astype(np.float32)
+    s = v[..., 0]
+    for k in range(1, 8):
+        s = (s + v[..., k]).astype(np.float32)
+    for k in range(i, w):
+        s = (s + win[..., k]).astype(np.float32)
+    return (s / np.float32(w)).astype(np.float32)
+
+
+def _stretch_corners_1d(m: np.ndarray, top: np.ndarray, bottom: np.ndarray, top_val: float = 1.0,
+                        bot_val: float = 0.0) -> np.ndarray:
+    """_stretch_corners, modulations.py:259-291, float32 operation by operation.  Anchors that came from a
+    tensor element (first / last sample) are float32, the corner targets are python floats; mixed arithmetic
+    rounds exactly like torch's scalar promotion (float / tensor is reciprocal(tensor) * float)."""
+    f32 = np.float32
+    n = m.shape[0]
+    anchors = [(int(i), f32(top_val)) for i in np.nonzero(top == 1)[0]] + \
+              [(int(i), f32(bot_val)) for i in np.nonzero(bottom == 1)[0]] + [(n - 1, m[-1])]
+    anchors.sort(key=lambda a: a[0])
+    out = m.copy()
+    prev_idx, prev_anchor = 0, m[0]
+    for idx, target in anchors:
+        seg = out[prev_idx + 1:idx + 1]
+        if prev_anchor != target:
+            curr_range = f32(abs(f32(m[prev_idx] - m[idx])))
+            target_range = f32(abs(f32(prev_anchor - target)))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                scale = f32(target_range / curr_range)
+                seg -= seg.min() if seg.size else f32(0)
+                seg *= scale
+                if seg.size:
+                    seg += f32(target - seg[-1])
+        prev_idx, prev_anchor = idx, target
+    return out
+
+
+def stretch_corners(mod_sig: np.ndarray, max_n_corners: int = 10, smooth_n_frames: int = 32) -> np.ndarray:
+    """stretch_corners, modulations.py:294-307."""
+    m = smoothen(_f32(mod_sig), smooth_n_frames)
+    assert m.ndim == 2
+    top, bottom = find_corners(m)
+    rows = []
+    for r in range(m.shape[0]):
+        if top[r].sum() + bottom[r].sum() > max_n_corners:
+            rows.append(m[r])
+        else:
+            rows.append(_stretch_corners_1d(m[r], top[r], bottom[r]))
+    return np.stack(rows, axis=0)
+
+
+def check_mod_sig(top: np.ndarray, bottom: np.ndarray, min_top_corners: int = 1, max_top_corners: int = 6,
+                  min_bottom_corners: int = 1, max_bottom_corners: int = 6,
+                  min_fraction_between_corners: float = 0.10) -> bool:
+    """check_mod_sig, modulations.py:311-345 (the signal itself only contributes its length)."""
+    n_top, n_bot = int(top.sum()), int(bottom.sum())
+    if n_top < min_top_corners or n_bot < min_bottom_corners:
+        return False
+    if n_top > max_top_corners or n_bot > max_bottom_corners:
+        return False
+    min_n_frames = int(min_fraction_between_corners * top.shape[0])
+    for c in (top, bottom):
+        idx = np.nonzero(c == 1)[0]
+        if idx.size > 1 and int(np.diff(idx).min()) < min_n_frames:
+            return False
+    return True
+
+
+def find_valid_mod_sig_indices(mod_sig: np.ndarray) -> List[int]:
+    """find_valid_mod_sig_indices, modulations.py:348-355."""
+    m = _f32(mod_sig)
+    top, bottom = find_corners(m)
+    return [r for r in range(m.shape[0]) if check_mod_sig(top[r], bottom[r])]

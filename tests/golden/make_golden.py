@@ -288,12 +288,60 @@ def gen_logmel():
     print(f"  hann: max|diff| = {np.abs(win_ref - oracle.hann_periodic(1024)).max():.3e}")
 
 
+def lfo_estimates(B, n, seed, noise):
+    """Signals shaped like the extractor's output: a 0.5-3 Hz cosine at the 172.5 Hz frame rate plus noise."""
+    g = tr.Generator().manual_seed(seed)
+    t = tr.arange(n) / 172.265625
+    f = tr.exp(tr.rand(B, 1, generator=g) * math.log(6.0)) * 0.5
+    ph = tr.rand(B, 1, generator=g) * 2 * math.pi
+    amp = 0.3 + 0.2 * tr.rand(B, 1, generator=g)
+    x = 0.5 + amp * tr.cos(2 * math.pi * f * t + ph) + noise * tr.randn(B, n, generator=g)
+    return tr.clip(x, 0.0, 1.0).float()
+
+
+def gen_postproc():
+    print("N4 smoothen / stretch_corners / find_valid_mod_sig_indices")
+    d = {}
+    k = 0
+    # (noise, max_n_corners, smooth_n_frames): the shipped settings are (16, 0) with an 8- or 4-frame model
+    # smoothing in front (configs/eval_em_unseen_effect.yml:95-100, eval_lfo.yml:126) and the defaults (10, 32)
+    for noise, mx, sm in [(0.0, 10, 32), (0.0, 16, 0), (0.003, 16, 8), (0.01, 10, 32), (0.01, 16, 8), (0.0, 6, 4),
+                          (0.05, 10, 32), (0.2, 16, 0)]:
+        x = lfo_estimates(24, 345, 100 + k, noise)
+        if k == 1:
+            x[3] = 0.25                      # flat row: no corners, first == last
+            x[4] = tr.linspace(0.1, 0.9, 345)  # ramp: no corners, one segment stretched onto itself
+        ref = rmod.stretch_corners(x.clone(), max_n_corners=mx, smooth_n_frames=sm)
+        got = oracle.stretch_corners(x.numpy(), mx, sm)
+        report(f"stretch_corners noise={noise} max={mx} smooth={sm}", ref.numpy(), got)
+        valid_in = rmod.find_valid_mod_sig_indices(rmod.smoothen(x, sm) if sm > 1 else x)
+        valid_out = rmod.find_valid_mod_sig_indices(ref)
+        assert valid_in == oracle.find_valid_mod_sig_indices(oracle.smoothen(x.numpy(), sm))
+        assert valid_out == oracle.find_valid_mod_sig_indices(ref.numpy())
+        print(f"    rows changed by the stretch: {int((ref != (rmod.smoothen(x, sm) if sm > 1 else x)).any(dim=1).sum())}/24, "
+              f"valid before/after: {len(valid_in)}/{len(valid_out)}")
+        d[f"x{k}"] = x.numpy()
+        d[f"cfg{k}"] = np.array([mx, sm])
+        d[f"y{k}"] = ref.numpy()
+        d[f"valid_in{k}"] = np.array(valid_in, dtype=np.int64)
+        d[f"valid_out{k}"] = np.array(valid_out, dtype=np.int64)
+        k += 1
+    d["n"] = np.array(k)
+    x = tr.rand((6, 345), generator=tr.Generator().manual_seed(77))
+    d["smooth_x"] = x.numpy()
+    for w in (4, 8, 16, 32, 5, 12):
+        ref = rmod.smoothen(x, w).numpy()
+        report(f"smoothen window={w}", ref, oracle.smoothen(x.numpy(), w))
+        d[f"smooth_y{w}"] = ref
+    np.savez_compressed(os.path.join(HERE, "postproc.npz"), **d)
+
+
 if __name__ == "__main__":
     tr.manual_seed(0)
     oracle.build()
-    which = sys.argv[1:] or ["lfo", "interp", "tremolo", "rng", "logmel", "fc"]
+    which = sys.argv[1:] or ["lfo", "interp", "tremolo", "rng", "logmel", "fc", "postproc"]
     fns = {"lfo": gen_lfo, "interp": gen_interp, "fc": gen_fc, "tremolo": gen_tremolo, "rng": gen_rng_lfos,
-           "logmel": gen_logmel}
+           "logmel": gen_logmel, "postproc": gen_postproc}
     for w in which:
         fns[w]()
     for f in sorted(os.listdir(HERE)):

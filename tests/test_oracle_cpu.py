@@ -120,3 +120,18 @@ def test_phaser_oracle_sanity():
     assert abs(float((y ** 2).sum() / (x ** 2).sum()) - 1.0) < 0.05
     y2 = oracle.phaser(np.concatenate([x, x]), 44100.0, 1.0, 0.5, 1000.0, 0.0, 1.0)
     assert np.array_equal(y2[:2], y)                        # examples are independent
+
+
+def test_postproc_oracle_bitwise():
+    """N4: smoothen / stretch_corners / find_valid_mod_sig_indices against the reference goldens."""
+    g = golden("postproc")
+    for k in range(int(g["n"])):
+        mx, sm = (int(v) for v in g[f"cfg{k}"])
+        x = g[f"x{k}"]
+        assert np.array_equal(oracle.stretch_corners(x, mx, sm), g[f"y{k}"], equal_nan=True), k
+        assert oracle.find_valid_mod_sig_indices(oracle.smoothen(x, sm)) == g[f"valid_in{k}"].tolist(), k
+        assert oracle.find_valid_mod_sig_indices(g[f"y{k}"]) == g[f"valid_out{k}"].tolist(), k
+    for w in (4, 8, 16, 32):
+        assert np.array_equal(oracle.smoothen(g["smooth_x"], w), g[f"smooth_y{w}"]), w
+    for w in (5, 12):       # torch's tail handling for windows that are not a multiple of 8 is not restated
+        assert np.abs(oracle.smoothen(g["smooth_x"], w) - g[f"smooth_y{w}"]).max() <= 2e-7, w
