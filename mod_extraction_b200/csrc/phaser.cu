@@ -136,42 +136,66 @@ __device__ __forceinline__ void cascade_retune(float (&w)[kStagesAP], float c_ol
     for (int k = 0; k < kStagesAP; ++k) w[k] *= r;
 }
 
+// Two runs of the cascade at once, one per half of a float2 (same coefficient): Blackwell's packed FFMA2 does the
+// work of two FFMAs in one issue slot, and the map kernel is bound by instruction issue.
+__device__ __forceinline__ float2 cascade_step2(float2 in, float2 (&w)[kStagesAP], float c) {
+    const float2 c2 = make_float2(c, c), nc2 = make_float2(-c, -c);
+    float2 v = in;
+#pragma unroll
+    for (int k = 0; k < kStagesAP; ++k) {
+        const float2 y = __ffma2_rn(c2, v, w[k]);
+        w[k] = __ffma2_rn(nc2, y, v);
+        v = y;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void cascade_retune2(float2 (&w)[kStagesAP], float c_old, float c_new) {
+    const float r = __fdividef(1.0f - c_new, 1.0f - c_old);
+    const float2 r2 = make_float2(r, r);
+#pragma unroll
+    for (int k = 0; k < kStagesAP; ++k) w[k] = __fmul2_rn(w[k], r2);
+}
+
 // ---- K1: per-chunk affine map ----------------------------------------------------------------
-// block = 256 threads = 8 warps; warp r performs run r (0..6: unit state e_r, no input; 7: zero state,
-// driven by x) for 32 consecutive chunks, lane = chunk.  The run index is warp-uniform, so the
-// homogeneous warps never touch the audio.
+// block = 128 threads = 4 warps; warp p performs runs 2p and 2p+1 packed in a float2 (runs 0..6: unit state
+// e_r, no input; run 7: zero state, driven by x) for 32 consecutive chunks, lane = chunk.  The run pair is
+// warp-uniform, so the homogeneous warps never touch the audio.
 template <bool DRIVEN>
-__device__ __forceinline__ void map_run(const float (*xs)[kChunk + 1], const float (*cs)[kCtl + 2], int ch, int len,
-                                        float fbk, float (&s)[kStagesAP], float& out_prev, int j_begin, float c_cur) {
+__device__ __forceinline__ void map_run2(const float (*xs)[kChunk + 1], const float (*cs)[kCtl + 2], int ch, int len,
+                                         float fbk, float2 (&s)[kStagesAP], float2& out_prev, int j_begin, float c_cur) {
     // j_begin is 0, or kUpd when the caller has already done the first control group by hand
-    // out_prev holds the previous cascade output; lastOutput = out_prev * feedback.
+    // out_prev holds the previous cascade outputs; lastOutput = out_prev * feedback.
     // cs[ch][0] is the coefficient of the sample before the chunk, cs[ch][1 + g] that of control group g.
+    const float2 nfb = make_float2(-fbk, -fbk);
     if (len == kChunk) {                       // full chunk: no guards, one coefficient per 4 samples
 #pragma unroll 2
         for (int g = j_begin / kUpd; g < kCtl; ++g) {
             const float c = cs[ch][1 + g];
-            cascade_retune(s, c_cur, c);
+            cascade_retune2(s, c_cur, c);
             c_cur = c;
 #pragma unroll
             for (int q = 0; q < kUpd; ++q) {
-                const float u = DRIVEN ? fmaf(-fbk, out_prev, xs[ch][g * kUpd + q]) : -fbk * out_prev;
-                out_prev = cascade_step(u, s, c);
+                const float2 u = DRIVEN ? __ffma2_rn(nfb, out_prev, make_float2(0.0f, xs[ch][g * kUpd + q]))
+                                        : __fmul2_rn(nfb, out_prev);
+                out_prev = cascade_step2(u, s, c);
             }
         }
     } else {
         for (int j = j_begin; j < len; ++j) {
             const float c = cs[ch][1 + (j >> 2)];
             if (c != c_cur) {
-                cascade_retune(s, c_cur, c);
+                cascade_retune2(s, c_cur, c);
                 c_cur = c;
             }
-            const float u = DRIVEN ? fmaf(-fbk, out_prev, xs[ch][j]) : -fbk * out_prev;
-            out_prev = cascade_step(u, s, c);
+            const float2 u = DRIVEN ? __ffma2_rn(nfb, out_prev, make_float2(0.0f, xs[ch][j])) : __fmul2_rn(nfb, out_prev);
+            out_prev = cascade_step2(u, s, c);
         }
     }
 }
 
-__global__ void __launch_bounds__(256) phaser_map_kernel(const PhaserArgs a, int n_super) {
+constexpr int kMapThreads = 128;
+__global__ void __launch_bounds__(kMapThreads) phaser_map_kernel(const PhaserArgs a, int n_super) {
     __shared__ float xs[32][kChunk + 1];
     __shared__ float cs[32][kCtl + 2];
     const int item = blockIdx.x / n_super, sc = blockIdx.x - item * n_super;
@@ -179,46 +203,49 @@ __global__ void __launch_bounds__(256) phaser_map_kernel(const PhaserArgs a, int
     const int tid = threadIdx.x;
     const int n_base = sc * 32 * kChunk;
     const float* xr = a.x + (int64_t)b * a.N;
-    for (int i = tid; i < 32 * kChunk; i += 256) {
+    for (int i = tid; i < 32 * kChunk; i += kMapThreads) {
         const int n = n_base + i;
         xs[i / kChunk][i % kChunk] = (n < a.N) ? xr[n] : 0.0f;
     }
     const float* cr = a.C + (int64_t)item * a.n_ctl;
-    for (int i = tid; i < 32 * (kCtl + 1); i += 256) {
+    for (int i = tid; i < 32 * (kCtl + 1); i += kMapThreads) {
         const int row = i / (kCtl + 1), col = i % (kCtl + 1);          // col 0 = coefficient before the chunk
         const int j = n_base / kUpd + row * kCtl + col - 1;
         cs[row][col] = cr[max(0, min(j, a.n_ctl - 1))];
     }
     __syncthreads();
-    const int run = tid >> 5, ch = tid & 31;
+    const int pair = tid >> 5, ch = tid & 31;
     const int chunk = sc * 32 + ch;
     if (chunk >= a.n_chunks) return;
     const int len = min(kChunk, a.N - chunk * kChunk);
     const float fbk = a.feedback[b];
-    float s[kStagesAP];
+    float2 s[kStagesAP];
 #pragma unroll
-    for (int k = 0; k < kStagesAP; ++k) s[k] = (run == k) ? 1.0f : 0.0f;
-    // state 6 is lastOutput = out_prev * feedback: a unit lastOutput is out_prev = 1 / feedback.  To stay
-    // finite for feedback = 0 the unit run carries `last` itself through the first sample.
-    float out_prev = 0.0f;
+    for (int k = 0; k < kStagesAP; ++k) s[k] = make_float2((2 * pair == k) ? 1.0f : 0.0f, (2 * pair + 1 == k) ? 1.0f : 0.0f);
+    float2 out_prev = make_float2(0.0f, 0.0f);
     const float c_prev = cs[ch][0];
-    if (run == 7) {
-        map_run<true>(xs, cs, ch, len, fbk, s, out_prev, 0, c_prev);
-    } else if (run == 6) {
-        // unit lastOutput: first control group by hand (u = -1 for the first sample); the all-pass states are
-        // zero before it, so there is nothing to retune
+    if (pair == 3) {
+        // runs 6 and 7.  State 6 is lastOutput = out_prev * feedback: a unit lastOutput is out_prev = 1 / feedback; to
+        // stay finite for feedback = 0 the unit run is fed u = -1 by hand for the first sample.  Both runs start
+        // with zero all-pass states, so there is nothing to retune before the first control group.
         const float c0 = cs[ch][1];
-        out_prev = cascade_step(-1.0f, s, c0);
+        out_prev = cascade_step2(make_float2(-1.0f, xs[ch][0]), s, c0);
         const int n0 = min(kUpd, len);
-        for (int q = 1; q < n0; ++q) out_prev = cascade_step(-fbk * out_prev, s, c0);
-        map_run<false>(xs, cs, ch, len, fbk, s, out_prev, kUpd, c0);
+        const float2 nfb = make_float2(-fbk, -fbk);
+        for (int q = 1; q < n0; ++q)
+            out_prev = cascade_step2(__ffma2_rn(nfb, out_prev, make_float2(0.0f, xs[ch][q])), s, c0);
+        map_run2<true>(xs, cs, ch, len, fbk, s, out_prev, kUpd, c0);
     } else {
-        map_run<false>(xs, cs, ch, len, fbk, s, out_prev, 0, c_prev);
+        map_run2<false>(xs, cs, ch, len, fbk, s, out_prev, 0, c_prev);
     }
-    float* m = a.Mw + ((int64_t)item * a.n_chunks + chunk) * kMapFloats + run * kState;
+    float* m = a.Mw + ((int64_t)item * a.n_chunks + chunk) * kMapFloats + 2 * pair * kState;
 #pragma unroll
-    for (int k = 0; k < kStagesAP; ++k) m[k] = s[k];
-    m[6] = out_prev * fbk;
+    for (int k = 0; k < kStagesAP; ++k) {
+        m[k] = s[k].x;
+        m[kState + k] = s[k].y;
+    }
+    m[6] = out_prev.x * fbk;
+    m[kState + 6] = out_prev.y * fbk;
 }
 
 // ---- K2: chain the maps: state at the start of every chunk --------------------------------------
@@ -312,6 +339,8 @@ __global__ void __launch_bounds__(256) phaser_chain_kernel(const float* __restri
 }
 
 // ---- K3: re-run every chunk from its true state, mix and clip --------------------------------------
+// (Packing two chunks per thread like K1 was measured: 0.56 ms instead of 0.36 ms for 1365 x 2 s, because it
+// halves the warps that hide the tile loads; this kernel is latency-bound, not issue-bound.)
 // One thread per chunk; a warp owns 32 consecutive chunks (16 KB of audio).  The audio moves through a
 // per-warp 32 x 32 shared tile: row i is filled by one coalesced 128-byte request (all lanes read chunk
 // i), then lane i walks row i.  That keeps every global request at one cache line (a lane-per-chunk
@@ -450,7 +479,7 @@ extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, 
     }
     {
         const int n_super = (a.n_chunks + 31) / 32;
-        phaser_map_kernel<<<(unsigned)((int64_t)a.n_items * n_super), 256, 0, s>>>(a, n_super);
+        phaser_map_kernel<<<(unsigned)((int64_t)a.n_items * n_super), kMapThreads, 0, s>>>(a, n_super);
     }
     if (a.n_chunks <= kSerialChainMax) {
         // short clips (689 maps for 2 s): one serial chain per example is the cheapest
