@@ -236,9 +236,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) logmel_kernel(const LogM
         int64_t row_n = 0;
         int it_n = 0;
         if (more) {
-            const int item_n = w / a.iters;
-            it_n = w - item_n * a.iters;
-            row_n = a.row_index ? a.row_index[item_n] : item_n;
+            if (a.by_row) {                         // same row, next group of frames
+                it_n = it + 1;
+                row_n = row;
+            } else {
+                const int item_n = w / a.iters;
+                it_n = w - item_n * a.iters;
+                row_n = a.row_index ? a.row_index[item_n] : item_n;
+            }
             bulk = stage_span(sbuf, a.x + row_n * a.x_row_stride, it_n * kFB * a.hop - kNfft / 2, T, span, tid, bar);
         }
         if (active) {
@@ -334,12 +339,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) logmel_kernel(const LogM
             const int live = min(kFB, a.n_frames - t0);
             const int t = tid & (kFB - 1);
             if (t < live) {
-                float* op = orow + (int64_t)(tid >> 3) * a.n_frames + t0 + t;
+                // band m = mb + 16 i lives in region m >> 7 at row m & 127; bit 2 of m (the half swap) is bit 2 of mb
+                const int mb = tid >> 3;
+                const float* ep = E + kStageOff + mb * kFB + (t ^ (mb & 4));
+                float* op = orow + (int64_t)mb * a.n_frames + t0 + t;
                 const int64_t ostep = (int64_t)(kThreads / kFB) * a.n_frames;
-#pragma unroll 4
-                for (int m = tid >> 3; m < a.n_mels; m += kThreads / kFB) {
-                    *op = E[(m / kStageBands) * kRegion + kStageOff + (m % kStageBands) * kFB + (t ^ ((m & 4)))];
+                static_assert(kStageBands == 128 && kThreads / kFB == 16, "store loop layout");
+#pragma unroll 8
+                for (int m = mb, i = 0; m < a.n_mels; m += kThreads / kFB, ++i) {
+                    *op = *ep;
                     op += ostep;
+                    ep += ((i & 7) == 7) ? (kRegion - 7 * 16 * kFB) : 16 * kFB;
                 }
             }
         }
