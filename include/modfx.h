@@ -187,6 +187,16 @@ int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T, int32_t n
                      const int32_t* row_index, int32_t n_index, void* stream);
 
 /*
+ * SpecAugment of the training forward, models.py:201-205 (torchaudio FrequencyMasking / TimeMasking with
+ * iid_masks=False: one band of mel bins [f0, f1) and one band of frames [t0, t1), the same for every row).
+ * The reference zeroes the mel power before clip + log; on the fused log-mel output (R, n_mels, n_frames)
+ * the masked cells are therefore set to log(eps) (is_log = 1) or to 0 (is_log = 0, mel power).  The two
+ * random draws per mask stay with the caller (torch global CPU generator).
+ */
+int modfx_specaugment_fill_f32(float* out, int64_t R, int32_t n_mels, int32_t n_frames, int32_t f0, int32_t f1,
+                               int32_t t0, int32_t t1, float eps, int32_t is_log, void* stream);
+
+/*
  * Replaces PedalboardPhaserDataset.apply_pedalboard_phaser's DSP, mod_extraction/datasets.py:455-482
  * (pedalboard.Phaser -> juce::dsp::Phaser, 6 TPT all-pass stages + feedback, cutoff updated every
  * 4th sample).  PARITY UNPINNED: checked only against this repo's own CPU restatement.
@@ -198,6 +208,48 @@ int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, c
                      const float* depth, const float* centre_hz, const float* feedback,
                      const float* mix, int32_t block, const int32_t* example_index, int32_t n_items,
                      void* workspace, void* stream);
+
+/*
+ * LFO-net body behind the log-mel front end: Spectral2DCNN.cnn, the mean over
+ * mel bins, the 1x1 output convolution and the sigmoid, mod_extraction/models.py:183-195,209-214.
+ * Activations between layers are channels-last float32: (B, H, W, C) with H = mel bins, W = frames.
+ *
+ *   modfx_cnn_layernorm_f32   replaces nn.LayerNorm([n_bins, n_frames], elementwise_affine=False),
+ *                             models.py:186: y = (x - mean) / sqrt(var + eps) per (b, c) over H x W
+ *                             (biased variance).  x is (B, C, H, W) when x_is_nchw (the log-mel tensor
+ *                             the front end writes) else (B, H, W, C); y is always (B, H, W, C) and may
+ *                             alias x when both are channels-last.  round_tf32 = 1 rounds y to TF32
+ *                             (round-to-nearest), the operand format of the tensor-core convolution.
+ *                             workspace: modfx_cnn_layernorm_workspace_bytes(B, C, H, W) bytes.
+ *   modfx_cnn_conv_pool_prelu_f32
+ *                             replaces Conv2d(Cin, Cout, (KH, KW), dilation=(1, dil_w), padding="same")
+ *                             -> MaxPool2d((2, 1)) -> PReLU(Cout), models.py:187-190.
+ *                             x (B, H, W, Cin) -> y (B, H/2, W, Cout).
+ *                             weight (KH, KW, Cout, Cin) float32 (the reference's (Cout, Cin, KH, KW)
+ *                             permuted), bias (Cout,), prelu (Cout,).
+ *                             precision MODFX_CNN_FP32: float32 FMAs on the CUDA cores (any Cin that
+ *                             is 2 or a multiple of 8); MODFX_CNN_TF32: tcgen05 tensor cores, TF32
+ *                             operands / float32 accumulation (Cin == 64; what cuDNN does for the
+ *                             reference on a GPU, torch.backends.cudnn.allow_tf32 defaults to True).
+ *                             Built: KH = 5, KW = 13, Cout = 64, H even.
+ *   modfx_cnn_head_f32        replaces tr.mean(x, dim=-2), Conv1d(C, L, 1) and tr.sigmoid,
+ *                             models.py:210-214: x (B, H, W, C) -> latent (B, C, W), out (B, L, W).
+ *                             weight (L, C), bias (L,).
+ */
+typedef enum {
+    MODFX_CNN_FP32 = 0,
+    MODFX_CNN_TF32 = 1
+} modfx_cnn_precision;
+
+int64_t modfx_cnn_layernorm_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+int modfx_cnn_layernorm_f32(const float* x, float* y, int32_t B, int32_t C, int32_t H, int32_t W,
+                            int32_t x_is_nchw, float eps, int32_t round_tf32, void* workspace, void* stream);
+int modfx_cnn_conv_pool_prelu_f32(const float* x, float* y, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                                  int32_t Cout, int32_t KH, int32_t KW, int32_t dil_w,
+                                  const float* weight, const float* bias, const float* prelu,
+                                  int32_t precision, void* stream);
+int modfx_cnn_head_f32(const float* x, float* latent, float* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                       int32_t L, const float* weight, const float* bias, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ class ModfxModSource(ctypes.Structure):
 
 
 MOD_AUDIO_RATE, MOD_CONTROL_RATE, MOD_LFO = 0, 1, 2
+CNN_FP32, CNN_TF32 = 0, 1      # modfx_cnn_precision
 
 SHAPES = ["cos", "rect_cos", "inv_rect_cos", "tri", "saw", "rsaw", "sqr"]   # modfx_shape order
 SHAPE_ID = {s: i for i, s in enumerate(SHAPES)}
@@ -67,6 +68,13 @@ _SIGNATURES = {
     "modfx_logmel_f32": ([_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.c_float, _i32,
                           _i64, _i64, _vp, _i32, _vp],
                          ctypes.c_int),
+    "modfx_specaugment_fill_f32": ([_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.c_float, _i32, _vp],
+                                   ctypes.c_int),
+    "modfx_cnn_layernorm_workspace_bytes": ([_i32, _i32, _i32, _i32], _i64),
+    "modfx_cnn_layernorm_f32": ([_vp, _vp, _i32, _i32, _i32, _i32, _i32, ctypes.c_float, _i32, _vp, _vp], ctypes.c_int),
+    "modfx_cnn_conv_pool_prelu_f32": ([_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp],
+                                      ctypes.c_int),
+    "modfx_cnn_head_f32": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], ctypes.c_int),
     "modfx_phaser_workspace_bytes": ([_i32, _i64], _i64),
     "modfx_phaser_f32": ([_vp, _vp, _i32, _i64, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp],
                          ctypes.c_int),

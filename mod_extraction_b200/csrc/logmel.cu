@@ -361,10 +361,39 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) logmel_kernel(const LogM
     }
 }
 
+// SpecAugment of the reference's training forward (models.py:201-205): torchaudio FrequencyMasking /
+// TimeMasking zero one band of mel bins and one band of frames of EVERY row between the mel power and
+// clip + log, so in the fused output the masked cells hold log(max(0, eps)).
+__global__ void specaugment_fill_kernel(float* __restrict__ out, int64_t n, int n_mels, int n_frames, int f0, int f1,
+                                        int t0, int t1, float fill) {
+    const int64_t per_row = (int64_t)n_mels * n_frames;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i % per_row;
+        const int m = (int)(e / n_frames), t = (int)(e - (int64_t)m * n_frames);
+        if ((m >= f0 && m < f1) || (t >= t0 && t < t1)) out[i] = fill;
+    }
+}
+
 }  // namespace
 }  // namespace modfx
 
 using namespace modfx;
+
+extern "C" int modfx_specaugment_fill_f32(float* out, int64_t R, int32_t n_mels, int32_t n_frames, int32_t f0,
+                                          int32_t f1, int32_t t0, int32_t t1, float eps, int32_t is_log, void* stream) {
+    MODFX_REQUIRE(out, "NULL pointer");
+    MODFX_REQUIRE(R >= 0 && n_mels >= 1 && n_frames >= 1, "bad shape");
+    MODFX_REQUIRE(0 <= f0 && f0 <= f1 && f1 <= n_mels && 0 <= t0 && t0 <= t1 && t1 <= n_frames, "bad mask bounds");
+    MODFX_REQUIRE(eps > 0.0f, "eps must be positive");
+    const int64_t n = R * n_mels * (int64_t)n_frames;
+    if (n == 0 || (f0 == f1 && t0 == t1)) return MODFX_OK;
+    // same arithmetic as the kernel's own log of a clipped zero: lg2.approx(eps) * ln 2
+    const float fill = is_log ? log2f(eps) * 0.69314718055994530942f : 0.0f;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
+    specaugment_fill_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, n, n_mels, n_frames, f0, f1, t0, t1, fill);
+    MODFX_CUDA_OK(cudaGetLastError());
+    return MODFX_OK;
+}
 
 extern "C" int modfx_logmel_f32(const float* x, float* out, int64_t R, int64_t T, int32_t n_fft, int32_t hop,
                                 int32_t n_mels, const float* window, const int32_t* fb_start,

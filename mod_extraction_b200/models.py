@@ -1,4 +1,4 @@
-"""Log-mel front end of the reference's LFO extractor, on the GPU.
+"""Log-mel front end and CNN body of the reference's LFO extractor (lfo_2dcnn), on the GPU.
 
 Reference: ``Spectral2DCNN`` builds ``self.spectrogram = MelSpectrogram(sample_rate=int(sr), n_fft,
 hop_length, normalized=False, n_mels, center=True)`` (models.py:170-175) and its ``forward`` does
@@ -8,12 +8,18 @@ hop_length, normalized=False, n_mels, center=True)`` (models.py:170-175) and its
 ``MelSpectrogram`` here is a drop-in for that ``spectrogram`` attribute (same constructor keywords,
 returns mel *power*, (..., T) -> (..., n_mels, T // hop + 1)); ``LogMelSpectrogram`` fuses the clip
 and log into the same kernel for inference, where no masking sits in between.
+
+``Spectral2DCNN`` is the whole extractor with the reference's constructor, ``forward(x) ->
+(sigmoid output, latent)`` and state-dict keys (models.py:127-215): log-mel kernel -> [SpecAugment fill when
+training] -> 6 x {layer norm, 5x13 dilated conv + 2x1 max-pool + PReLU} -> mean over mel -> 1x1 conv -> sigmoid,
+activations channels-last, the 64->64 convolutions on tcgen05 tensor cores (TF32, like cuDNN's default for the
+reference on a GPU) or, with ``precision="fp32"``, on the CUDA cores.  Inference only (no autograd).
 """
 from __future__ import annotations
 
 import ctypes
 import math
-from typing import Optional, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -21,7 +27,7 @@ from torch import Tensor, nn
 
 from . import _lib
 
-__all__ = ["MelSpectrogram", "LogMelSpectrogram", "mel_filterbank", "banded"]
+__all__ = ["MelSpectrogram", "LogMelSpectrogram", "Spectral2DCNN", "mel_filterbank", "banded"]
 
 
 def _hz_to_mel(f: float) -> float:
@@ -147,3 +153,167 @@ class LogMelSpectrogram(MelSpectrogram):
     """``log(clip(MelSpectrogram(x), min=eps))`` in one kernel (models.py:199,207-208)."""
 
     apply_log = True
+
+
+def _vp(t: Optional[Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round_to_tf32(w: Tensor) -> Tensor:
+    """Round float32 to the nearest TF32 value (10-bit mantissa, ties away from zero like cvt.rna.tf32.f32):
+    the tensor cores ignore the low 13 mantissa bits of their operands, i.e. they would truncate."""
+    bits = w.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def specaugment_bounds(size: int, mask_param: int) -> Tuple[int, int]:
+    """The two draws of torchaudio.functional.mask_along_axis (torch global CPU generator, this order):
+    ``value = rand(1) * mask_param; min_value = rand(1) * (size - value)`` -> [start, end)."""
+    if mask_param < 1:
+        return 0, 0
+    value = torch.rand(1) * mask_param
+    min_value = torch.rand(1) * (size - value)
+    start = int(min_value.long())
+    end = start + int(value.long())
+    return start, end
+
+
+class Spectral2DCNN(nn.Module):
+    """GPU drop-in for ``mod_extraction.models.Spectral2DCNN`` (models.py:127-215), inference only.
+
+    Same constructor arguments, same ``forward(x) -> (x, latent)`` with x (B, in_ch, n_samples) ->
+    (B, latent_dim, n_frames) and latent (B, out_channels[-1], n_frames), and the same parameter names, so
+    ``load_state_dict`` takes a reference checkpoint unchanged (the torch sub-modules below only hold the
+    parameters; the arithmetic runs in libmodfx).  ``precision``: "tf32" (tcgen05, default) or "fp32".
+    Built: kernel_size (5, 13), pool_size (2, 1), 64 channels per layer, bin dilation 1, use_ln=True.
+    """
+
+    def __init__(self, in_ch: int = 1, n_samples: int = 88200, sr: float = 44100, n_fft: int = 1024,
+                 hop_len: int = 256, n_mels: int = 256, kernel_size: Tuple[int, int] = (5, 13),
+                 out_channels: Optional[List[int]] = None, bin_dilations: Optional[List[int]] = None,
+                 temp_dilations: Optional[List[int]] = None, pool_size: Tuple[int, int] = (3, 1),
+                 latent_dim: int = 1, freq_mask_amount: float = 0.0, time_mask_amount: float = 0.0,
+                 use_ln: bool = True, eps: float = 1e-7, precision: str = "tf32") -> None:
+        super().__init__()
+        assert pool_size[1] == 1
+        if out_channels is None:
+            out_channels = [64] * 5
+        if bin_dilations is None:
+            bin_dilations = [1] * len(out_channels)
+        if temp_dilations is None:
+            temp_dilations = [2 ** idx for idx in range(len(out_channels))]
+        assert len(out_channels) == len(bin_dilations) == len(temp_dilations)
+        if tuple(kernel_size) != (5, 13) or tuple(pool_size) != (2, 1) or any(c != 64 for c in out_channels) \
+                or any(d != 1 for d in bin_dilations) or not use_ln or in_ch != 2:
+            raise NotImplementedError(
+                "modfx builds the shipped lfo_2dcnn (configs/models/spectral_2dcnn.yml): in_ch 2, kernel (5, 13), "
+                "pool (2, 1), 64 channels per layer, bin dilation 1, use_ln")
+        assert n_mels % (2 ** len(out_channels)) == 0, "n_mels must survive the 2x1 pools"
+        assert precision in ("tf32", "fp32")
+        self.in_ch, self.n_samples, self.sr, self.n_fft, self.hop_len, self.n_mels = in_ch, n_samples, sr, n_fft, hop_len, n_mels
+        self.kernel_size, self.pool_size, self.latent_dim = tuple(kernel_size), tuple(pool_size), latent_dim
+        self.freq_mask_amount, self.time_mask_amount, self.use_ln, self.eps = freq_mask_amount, time_mask_amount, use_ln, eps
+        self.out_channels, self.bin_dilations, self.temp_dilations = list(out_channels), list(bin_dilations), list(temp_dilations)
+        self.precision = precision
+        self.ln_eps = 1e-5                        # nn.LayerNorm default (models.py:186)
+
+        self.spectrogram = LogMelSpectrogram(sample_rate=int(sr), n_fft=n_fft, hop_length=hop_len, n_mels=n_mels, eps=eps)
+        n_frames = n_samples // hop_len + 1
+        self.freq_mask_param = int(freq_mask_amount * n_mels)          # models.py:180
+        self.time_mask_param = int(time_mask_amount * n_frames)        # models.py:181
+        # parameter containers with the reference's module indices (LayerNorm, Conv2d, MaxPool2d, PReLU per layer)
+        layers: List[nn.Module] = []
+        n_bins, c_in = n_mels, in_ch
+        for out_ch, t_dil in zip(out_channels, temp_dilations):
+            layers.append(nn.LayerNorm([n_bins, n_frames], elementwise_affine=False))
+            layers.append(nn.Conv2d(c_in, out_ch, kernel_size, stride=(1, 1), dilation=(1, t_dil), padding="same"))
+            layers.append(nn.MaxPool2d(kernel_size=pool_size))
+            layers.append(nn.PReLU(num_parameters=out_ch))
+            c_in = out_ch
+            n_bins //= pool_size[0]
+        self.cnn = nn.Sequential(*layers)
+        self.output = nn.Conv1d(out_channels[-1], latent_dim, kernel_size=(1,))
+        self._packed = None
+        self._packed_key = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Accepts a reference checkpoint as is: its ``spectrogram.*`` buffers (torchaudio's window and mel table,
+        models.py:170-175) are not parameters here -- they rebuild the front end instead."""
+        sd = dict(state_dict)
+        fb = sd.pop("spectrogram.mel_scale.fb", None)
+        window = sd.pop("spectrogram.spectrogram.window", None)
+        if fb is not None or window is not None:
+            self.spectrogram = LogMelSpectrogram(sample_rate=int(self.sr), n_fft=self.n_fft, hop_length=self.hop_len,
+                                                 n_mels=self.n_mels, eps=self.eps, fb=fb, window=window)
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    # ---- weights in the layout the kernels read: (KH, KW, Cout, Cin), TF32-rounded for the tensor-core layers
+    def _pack(self, device) -> list:
+        params = list(self.parameters())
+        key = (str(device), self.precision) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or self._packed_key != key:
+            packed = []
+            for i in range(len(self.out_channels)):
+                conv, act = self.cnn[4 * i + 1], self.cnn[4 * i + 3]
+                w = conv.weight.detach().to(device=device, dtype=torch.float32).permute(2, 3, 0, 1).contiguous()
+                tc = self.precision == "tf32" and w.size(3) == 64
+                if tc:
+                    w = round_to_tf32(w)
+                packed.append((w, conv.bias.detach().to(device=device, dtype=torch.float32).contiguous(),
+                               act.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
+                               _lib.CNN_TF32 if tc else _lib.CNN_FP32))
+            w_out = self.output.weight.detach().to(device=device, dtype=torch.float32).reshape(self.latent_dim, -1).contiguous()
+            b_out = self.output.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+            self._packed, self._packed_key = (packed, w_out, b_out), key
+        return self._packed
+
+    @torch.no_grad()
+    def forward_features(self, logmel: Tensor) -> Tuple[Tensor, Tensor]:
+        """(B, in_ch, n_mels, n_frames) log-mel (clip + log already applied) -> (output, latent)."""
+        if not logmel.is_cuda:
+            raise RuntimeError("modfx: Spectral2DCNN needs CUDA tensors (no CPU kernel)")
+        L = _lib.lib()
+        dev = logmel.device
+        logmel = logmel.detach().float().contiguous()
+        B, C, H, W = logmel.shape
+        assert C == self.in_ch and H == self.n_mels
+        packed, w_out, b_out = self._pack(dev)
+        with torch.cuda.device(dev):
+            ws_bytes = max(L.modfx_cnn_layernorm_workspace_bytes(B, C, H, W), L.modfx_cnn_layernorm_workspace_bytes(B, 64, H // 2, W))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            x = torch.empty((B, H, W, C), dtype=torch.float32, device=dev)
+            _lib.check(L.modfx_cnn_layernorm_f32(_vp(logmel), _vp(x), B, C, H, W, 1, self.ln_eps, 0, _vp(ws), _stream()))
+            for i, (w, bias, slope, prec) in enumerate(packed):
+                y = torch.empty((B, H // 2, W, 64), dtype=torch.float32, device=dev)
+                _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(x), _vp(y), B, H, W, C, 64, 5, 13, self.temp_dilations[i],
+                                                          _vp(w), _vp(bias), _vp(slope), prec, _stream()))
+                H, C, x = H // 2, 64, y
+                if i + 1 < len(packed):
+                    nxt_tc = packed[i + 1][3] == _lib.CNN_TF32
+                    _lib.check(L.modfx_cnn_layernorm_f32(_vp(x), _vp(x), B, C, H, W, 0, self.ln_eps, 1 if nxt_tc else 0,
+                                                        _vp(ws), _stream()))
+            latent = torch.empty((B, C, W), dtype=torch.float32, device=dev)
+            out = torch.empty((B, self.latent_dim, W), dtype=torch.float32, device=dev)
+            _lib.check(L.modfx_cnn_head_f32(_vp(x), _vp(latent), _vp(out), B, H, W, C, self.latent_dim, _vp(w_out), _vp(b_out),
+                                           _stream()))
+        return out, latent
+
+    @torch.no_grad()
+    def forward(self, x: Tensor) -> Tuple[Tensor, Tensor]:
+        assert x.ndim == 3
+        logmel = self.spectrogram(x)                               # models.py:199,207-208 fused
+        if self.training:                                          # models.py:201-205
+            f0 = f1 = t0 = t1 = 0
+            if self.freq_mask_amount > 0:
+                f0, f1 = specaugment_bounds(logmel.size(-2), self.freq_mask_param)
+            if self.time_mask_amount > 0:
+                t0, t1 = specaugment_bounds(logmel.size(-1), self.time_mask_param)
+            with torch.cuda.device(logmel.device):
+                _lib.check(_lib.lib().modfx_specaugment_fill_f32(
+                    _vp(logmel), logmel.size(0) * logmel.size(1), logmel.size(-2), logmel.size(-1), f0, f1, t0, t1,
+                    float(self.eps), 1, _stream()))
+        return self.forward_features(logmel)

@@ -493,3 +493,66 @@ def find_valid_mod_sig_indices(mod_sig: np.ndarray) -> List[int]:
     m = _f32(mod_sig)
     top, bottom = find_corners(m)
     return [r for r in range(m.shape[0]) if check_mod_sig(top[r], bottom[r])]
+
+
+# ---- LFO-net body, models.py:183-195,209-214 (numpy float32) ----------------------------
+def layer_norm_2d(x: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """nn.LayerNorm([H, W], elementwise_affine=False), models.py:186: per (b, c) over the last two dims,
+    biased variance.  x (B, C, H, W)."""
+    x = _f32(x)
+    mean = x.mean(axis=(-2, -1), keepdims=True, dtype=np.float64)
+    var = ((x.astype(np.float64) - mean) ** 2).mean(axis=(-2, -1), keepdims=True)
+    return ((x - mean) / np.sqrt(var + eps)).astype(np.float32)
+
+
+def conv2d_same(x: np.ndarray, weight: np.ndarray, bias: np.ndarray, dil_w: int = 1, tf32: bool = False) -> np.ndarray:
+    """nn.Conv2d(Cin, Cout, (KH, KW), dilation=(1, dil_w), padding="same"), models.py:187.
+    x (B, Cin, H, W), weight (Cout, Cin, KH, KW).  One float32 GEMM per kernel tap; ``tf32`` rounds both
+    operands to 10 mantissa bits first (what the tensor-core path feeds its MMAs)."""
+    x, weight = _f32(x), _f32(weight)
+    if tf32:
+        x, weight = round_tf32(x), round_tf32(weight)
+    B, Cin, H, W = x.shape
+    Cout, _, KH, KW = weight.shape
+    ph, pw = KH // 2, (KW // 2) * dil_w
+    xp = np.zeros((B, Cin, H + 2 * ph, W + 2 * pw), dtype=np.float32)
+    xp[:, :, ph:ph + H, pw:pw + W] = x
+    out = np.zeros((B, Cout, H, W), dtype=np.float32)
+    for kh in range(KH):
+        for kw in range(KW):
+            win = xp[:, :, kh:kh + H, kw * dil_w:kw * dil_w + W]              # (B, Cin, H, W)
+            out += np.einsum("oc,bchw->bohw", weight[:, :, kh, kw], win, optimize=True).astype(np.float32)
+    return out + _f32(bias)[None, :, None, None]
+
+
+def round_tf32(a: np.ndarray) -> np.ndarray:
+    """float32 -> nearest TF32 (ties away from zero, cvt.rna.tf32.f32)."""
+    bits = _f32(a).view(np.int32)
+    return ((bits + 0x1000) & ~0x1FFF).astype(np.int32).view(np.float32)
+
+
+def max_pool_h2(x: np.ndarray) -> np.ndarray:
+    """nn.MaxPool2d((2, 1)), models.py:188."""
+    B, C, H, W = x.shape
+    return x[:, :, :H - (H % 2)].reshape(B, C, H // 2, 2, W).max(axis=3)
+
+
+def prelu(x: np.ndarray, slope: np.ndarray) -> np.ndarray:
+    """nn.PReLU(num_parameters=C), models.py:189."""
+    return np.where(x > 0, x, _f32(slope)[None, :, None, None] * x).astype(np.float32)
+
+
+def spectral_2dcnn_body(logmel: np.ndarray, convs, out_w: np.ndarray, out_b: np.ndarray, temp_dilations,
+                        ln_eps: float = 1e-5, tf32_from_layer: Optional[int] = None):
+    """Spectral2DCNN.forward after clip + log, models.py:209-214.
+    logmel (B, C, n_mels, n_frames); convs = [(weight (Cout, Cin, KH, KW), bias, prelu slope), ...];
+    out_w (L, C), out_b (L,).  Returns (sigmoid output (B, L, W), latent (B, C, W)).
+    ``tf32_from_layer`` = index of the first layer whose operands are TF32-rounded (None: float32 all the way)."""
+    x = _f32(logmel)
+    for i, ((w, b, a), d) in enumerate(zip(convs, temp_dilations)):
+        x = layer_norm_2d(x, ln_eps)
+        x = conv2d_same(x, w, b, d, tf32=tf32_from_layer is not None and i >= tf32_from_layer)
+        x = prelu(max_pool_h2(x), a)
+    latent = x.mean(axis=-2, dtype=np.float32)
+    z = np.einsum("lc,bcw->blw", _f32(out_w), latent).astype(np.float32) + _f32(out_b)[None, :, None]
+    return (1.0 / (1.0 + np.exp(-z))).astype(np.float32), latent

@@ -336,12 +336,68 @@ def gen_postproc():
     np.savez_compressed(os.path.join(HERE, "postproc.npz"), **d)
 
 
+def gen_cnn():
+    """N3: Spectral2DCNN (models.py:127-215) with seeded weights (tests/helpers.cnn_weights)."""
+    print("N3 Spectral2DCNN body")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+
+    def make(n_samples, n_mels, seed):
+        net = rmodels.Spectral2DCNN(in_ch=2, n_samples=n_samples, sr=SR, n_mels=n_mels, kernel_size=(5, 13),
+                                    out_channels=[64] * 6, temp_dilations=helpers.CNN_DILATIONS, pool_size=(2, 1),
+                                    latent_dim=1, freq_mask_amount=0.25, time_mask_amount=0.25, use_ln=True)
+        sd = helpers.cnn_weights(seed)
+        missing = net.load_state_dict({k: tr.from_numpy(v) for k, v in sd.items()}, strict=False)
+        assert not missing.unexpected_keys and all(k.startswith("spectrogram.") for k in missing.missing_keys)
+        return net, sd
+
+    d = {}
+    # (a) reduced shape: 8192 samples, 64 mel bins -> 33 frames, final map 1 x 33
+    net, sd = make(8192, 64, 7)
+    net.eval()
+    x = tr.cat([white((3, 1, 8192), 51), guitar(3, 8192, 52)], dim=1)
+    with tr.no_grad():
+        lm = tr.log(tr.clip(net.spectrogram(x), min=net.eps))
+        y, lat = net(x)
+    convs, ow, ob = helpers.cnn_oracle_args(sd)
+    yo, lo = oracle.spectral_2dcnn_body(lm.numpy(), convs, ow, ob, helpers.CNN_DILATIONS)
+    report("small: oracle fp32 output", y.numpy(), yo)
+    report("small: oracle fp32 latent", lat.numpy(), lo)
+    yo, lo = oracle.spectral_2dcnn_body(lm.numpy(), convs, ow, ob, helpers.CNN_DILATIONS, tf32_from_layer=1)
+    report("small: oracle tf32 output", y.numpy(), yo)
+    report("small: oracle tf32 latent", lat.numpy(), lo)
+    d.update(small_x=x.numpy(), small_logmel=lm.numpy(), small_y=y.numpy(), small_latent=lat.numpy(),
+             small_fb=net.spectrogram.mel_scale.fb.numpy())
+    # (b) the same network in training mode: SpecAugment masks from the torch global generator (models.py:201-205)
+    net.train()
+    tr.manual_seed(1234)
+    with tr.no_grad():
+        y, lat = net(x)
+    d.update(train_seed=np.array(1234), train_y=y.numpy(), train_latent=lat.numpy())
+    # (c) the shipped shape: 88200 samples, 256 mel bins -> (B, 1, 345)
+    net, sd = make(88200, 256, 8)
+    net.eval()
+    x = tr.cat([white((2, 1, 88200), 53), guitar(2, 88200, 54)], dim=1)
+    with tr.no_grad():
+        lm = tr.log(tr.clip(net.spectrogram(x), min=net.eps))
+        y, lat = net(x)
+    convs, ow, ob = helpers.cnn_oracle_args(sd)
+    yo, lo = oracle.spectral_2dcnn_body(lm.numpy(), convs, ow, ob, helpers.CNN_DILATIONS)
+    report("full: oracle fp32 output", y.numpy(), yo)
+    report("full: oracle fp32 latent", lat.numpy(), lo)
+    yo, lo = oracle.spectral_2dcnn_body(lm.numpy(), convs, ow, ob, helpers.CNN_DILATIONS, tf32_from_layer=1)
+    report("full: oracle tf32 output", y.numpy(), yo)
+    report("full: oracle tf32 latent", lat.numpy(), lo)
+    d.update(full_x_seeds=np.array([53, 54]), full_x_probe=x.numpy()[..., ::4410], full_y=y.numpy(), full_latent=lat.numpy())
+    np.savez_compressed(os.path.join(HERE, "cnn.npz"), **d)
+
+
 if __name__ == "__main__":
     tr.manual_seed(0)
     oracle.build()
-    which = sys.argv[1:] or ["lfo", "interp", "tremolo", "rng", "logmel", "fc", "postproc"]
+    which = sys.argv[1:] or ["lfo", "interp", "tremolo", "rng", "logmel", "fc", "postproc", "cnn"]
     fns = {"lfo": gen_lfo, "interp": gen_interp, "fc": gen_fc, "tremolo": gen_tremolo, "rng": gen_rng_lfos,
-           "logmel": gen_logmel, "postproc": gen_postproc}
+           "logmel": gen_logmel, "postproc": gen_postproc, "cnn": gen_cnn}
     for w in which:
         fns[w]()
     for f in sorted(os.listdir(HERE)):

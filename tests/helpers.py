@@ -49,3 +49,30 @@ def fc_params_from_golden(g, k):
         params.append(float(p) if p.ndim == 0 else p.astype(np.float32))
         j += 1
     return params
+
+
+CNN_DILATIONS = [1, 1, 2, 4, 8, 16]       # configs/models/spectral_2dcnn.yml
+
+
+def cnn_weights(seed, in_ch=2, n_layers=6, ch=64, kh=5, kw=13, latent_dim=1):
+    """Seeded random weights for Spectral2DCNN as a state-dict of numpy arrays (reference key names,
+    models.py:183-195): lively enough that every layer matters (fan-in scaled convs, PReLU slopes 0.05..0.4)."""
+    rng = np.random.RandomState(seed)
+    sd = {}
+    c_in = in_ch
+    for i in range(n_layers):
+        bound = 1.7 / math.sqrt(c_in * kh * kw)
+        sd[f"cnn.{4 * i + 1}.weight"] = rng.uniform(-bound, bound, (ch, c_in, kh, kw)).astype(np.float32)
+        sd[f"cnn.{4 * i + 1}.bias"] = rng.uniform(-0.1, 0.1, (ch,)).astype(np.float32)
+        sd[f"cnn.{4 * i + 3}.weight"] = rng.uniform(0.05, 0.4, (ch,)).astype(np.float32)
+        c_in = ch
+    sd["output.weight"] = rng.uniform(-0.5, 0.5, (latent_dim, ch, 1)).astype(np.float32)
+    sd["output.bias"] = rng.uniform(-0.1, 0.1, (latent_dim,)).astype(np.float32)
+    return sd
+
+
+def cnn_oracle_args(sd, n_layers=6):
+    """cnn_weights() -> the (convs, out_w, out_b) arguments of oracle.spectral_2dcnn_body."""
+    convs = [(sd[f"cnn.{4 * i + 1}.weight"], sd[f"cnn.{4 * i + 1}.bias"], sd[f"cnn.{4 * i + 3}.weight"])
+             for i in range(n_layers)]
+    return convs, sd["output.weight"][:, :, 0], sd["output.bias"]

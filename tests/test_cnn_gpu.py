@@ -1,0 +1,232 @@
+"""N3: the LFO-net body behind the log-mel front end -- layer norm, 5x13 dilated conv + max-pool +
+PReLU (CUDA-core float32 and tcgen05 TF32), head -- against the reference goldens (tests/golden/cnn.npz, made by
+mod_extraction.models.Spectral2DCNN itself) and the numpy oracle.
+
+Tolerances (written out because this is floating point):
+* float32 path, body fed with the reference's own log-mel: output <= 2e-5, latent <= 1e-4 (summation order only);
+* float32 path end to end (own log-mel kernel in front): output <= 2e-4, latent <= 1e-3;
+* TF32 tensor-core path: output <= 3e-3, latent <= 1e-2 -- TF32 operands carry 10 mantissa bits; the oracle with
+  TF32-rounded operands is itself 6e-4 / 1.8e-3 from the float32 reference.  A single tensor-core layer agrees
+  with the CUDA-core kernel on identical TF32 operands to 1e-4 (measured 5e-5: the MMA's float32 accumulation is
+  not IEEE-rounded); through six layers the TF32 re-rounding of activations amplifies that, so the whole body is
+  held to 5e-4 / 2e-3 against the TF32 oracle (measured 1.6e-4).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import CNN_DILATIONS, cnn_oracle_args, cnn_weights, golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+SR = 44100
+
+
+def t_white(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(shape, generator=g) * 2.0 - 1.0) * 0.5
+
+
+def t_guitar(B, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(N, dtype=torch.float64) / SR
+    out = []
+    for b in range(B):
+        f0 = 110.0 * (1.0 + 0.25 * b)
+        sig = sum((0.3 / k) * torch.sin(2 * math.pi * f0 * k * t) * torch.exp(-k * t) for k in range(1, 9))
+        out.append(sig.float() + 1e-3 * torch.randn(N, generator=g))
+    return torch.stack(out, 0).unsqueeze(1)
+
+
+def make_net(n_samples, n_mels, seed, precision, fb=None):
+    from mod_extraction_b200.models import LogMelSpectrogram, Spectral2DCNN
+    net = Spectral2DCNN(in_ch=2, n_samples=n_samples, sr=SR, n_mels=n_mels, kernel_size=(5, 13), out_channels=[64] * 6,
+                        temp_dilations=CNN_DILATIONS, pool_size=(2, 1), latent_dim=1, freq_mask_amount=0.25,
+                        time_mask_amount=0.25, use_ln=True, precision=precision)
+    sd = cnn_weights(seed)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    if fb is not None:      # the goldens carry the reference's own mel table
+        net.spectrogram = LogMelSpectrogram(sample_rate=SR, n_mels=n_mels, fb=torch.from_numpy(fb))
+    return net.to(DEV).eval(), sd
+
+
+def maxdiff(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).max())
+
+
+def test_layernorm_both_layouts():
+    from mod_extraction_b200 import _lib
+    from mod_extraction_b200.models import _stream, _vp
+    from oracle import oracle
+    L = _lib.lib()
+    rng = np.random.RandomState(3)
+    for (B, C, H, W) in [(3, 2, 64, 33), (2, 64, 16, 345), (1, 2, 256, 345)]:
+        x = (rng.standard_normal((B, C, H, W)) * 3.0 + 1.5).astype(np.float32)
+        ref = oracle.layer_norm_2d(x).transpose(0, 2, 3, 1)
+        ws = torch.empty(L.modfx_cnn_layernorm_workspace_bytes(B, C, H, W), dtype=torch.uint8, device=DEV)
+        xd = torch.from_numpy(x).to(DEV)
+        y = torch.empty((B, H, W, C), device=DEV)
+        _lib.check(L.modfx_cnn_layernorm_f32(_vp(xd), _vp(y), B, C, H, W, 1, 1e-5, 0, _vp(ws), _stream()))
+        assert maxdiff(y.cpu().numpy(), ref) <= 2e-6
+        xl = xd.permute(0, 2, 3, 1).contiguous()
+        _lib.check(L.modfx_cnn_layernorm_f32(_vp(xl), _vp(xl), B, C, H, W, 0, 1e-5, 0, _vp(ws), _stream()))   # in place
+        assert maxdiff(xl.cpu().numpy(), ref) <= 2e-6
+        xl = xd.permute(0, 2, 3, 1).contiguous()
+        _lib.check(L.modfx_cnn_layernorm_f32(_vp(xl), _vp(xl), B, C, H, W, 0, 1e-5, 1, _vp(ws), _stream()))   # TF32 rounding
+        got = xl.cpu().numpy()
+        assert np.array_equal(got, oracle.round_tf32(got)) and maxdiff(got, ref) <= 4e-3
+
+
+@pytest.mark.parametrize("cin,dil,H,W", [(2, 1, 8, 33), (64, 1, 4, 33), (64, 4, 6, 130), (64, 16, 8, 345), (64, 2, 2, 7)])
+def test_conv_pool_prelu_fp32_vs_oracle(cin, dil, H, W):
+    from mod_extraction_b200 import _lib
+    from mod_extraction_b200.models import _stream, _vp
+    from oracle import oracle
+    L = _lib.lib()
+    rng = np.random.RandomState(cin + dil)
+    B = 2
+    x = rng.standard_normal((B, cin, H, W)).astype(np.float32)
+    w = (rng.standard_normal((64, cin, 5, 13)) / math.sqrt(cin * 65)).astype(np.float32)
+    bias = rng.uniform(-0.2, 0.2, 64).astype(np.float32)
+    slope = rng.uniform(0.05, 0.4, 64).astype(np.float32)
+    ref = oracle.prelu(oracle.max_pool_h2(oracle.conv2d_same(x, w, bias, dil)), slope).transpose(0, 2, 3, 1)
+    xd = torch.from_numpy(x).to(DEV).permute(0, 2, 3, 1).contiguous()
+    wd = torch.from_numpy(w).to(DEV).permute(2, 3, 0, 1).contiguous()
+    y = torch.empty((B, H // 2, W, 64), device=DEV)
+    bd, sd = torch.from_numpy(bias).to(DEV), torch.from_numpy(slope).to(DEV)      # kept alive across the launch
+    _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(xd), _vp(y), B, H, W, cin, 64, 5, 13, dil, _vp(wd), _vp(bd), _vp(sd),
+                                               _lib.CNN_FP32, _stream()))
+    assert maxdiff(y.cpu().numpy(), ref) <= 2e-5
+
+
+@pytest.mark.parametrize("dil,H,W,B", [(1, 4, 33, 2), (1, 2, 128, 1), (2, 6, 130, 2), (4, 8, 345, 2), (16, 8, 345, 3),
+                                       (8, 16, 345, 1)])
+def test_conv_pool_prelu_tcgen05_vs_fp32_kernel_and_oracle(dil, H, W, B):
+    """The tensor-core convolution against (a) the CUDA-core kernel fed the same TF32-rounded operands: only the
+    accumulation order differs, (b) the numpy oracle."""
+    from mod_extraction_b200 import _lib
+    from mod_extraction_b200.models import _stream, _vp, round_to_tf32
+    from oracle import oracle
+    L = _lib.lib()
+    rng = np.random.RandomState(100 + dil + W)
+    x = rng.standard_normal((B, 64, H, W)).astype(np.float32)
+    w = (rng.standard_normal((64, 64, 5, 13)) / math.sqrt(64 * 65)).astype(np.float32)
+    bias = rng.uniform(-0.2, 0.2, 64).astype(np.float32)
+    slope = rng.uniform(0.05, 0.4, 64).astype(np.float32)
+    xd = round_to_tf32(torch.from_numpy(x).to(DEV).permute(0, 2, 3, 1).contiguous())
+    wd = round_to_tf32(torch.from_numpy(w).to(DEV).permute(2, 3, 0, 1).contiguous())
+    bd, sd = torch.from_numpy(bias).to(DEV), torch.from_numpy(slope).to(DEV)
+    y_tc = torch.full((B, H // 2, W, 64), float("nan"), device=DEV)
+    y_cc = torch.empty((B, H // 2, W, 64), device=DEV)
+    _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(xd), _vp(y_tc), B, H, W, 64, 64, 5, 13, dil, _vp(wd), _vp(bd), _vp(sd),
+                                               _lib.CNN_TF32, _stream()))
+    _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(xd), _vp(y_cc), B, H, W, 64, 64, 5, 13, dil, _vp(wd), _vp(bd), _vp(sd),
+                                               _lib.CNN_FP32, _stream()))
+    torch.cuda.synchronize()
+    got = y_tc.cpu().numpy()
+    assert np.isfinite(got).all(), "tensor-core kernel left outputs unwritten"
+    assert maxdiff(got, y_cc.cpu().numpy()) <= 1e-4
+    ref = oracle.prelu(oracle.max_pool_h2(oracle.conv2d_same(x, w, bias, dil, tf32=True)), slope).transpose(0, 2, 3, 1)
+    assert maxdiff(got, ref) <= 1e-4
+
+
+def test_head_vs_oracle():
+    from mod_extraction_b200 import _lib
+    from mod_extraction_b200.models import _stream, _vp
+    L = _lib.lib()
+    rng = np.random.RandomState(5)
+    B, H, W, C, Ld = 3, 4, 345, 64, 2
+    x = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    w = rng.uniform(-0.5, 0.5, (Ld, C)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, Ld).astype(np.float32)
+    lat_ref = x.mean(axis=1).transpose(0, 2, 1)
+    out_ref = 1.0 / (1.0 + np.exp(-(np.einsum("lc,bcw->blw", w, lat_ref) + b[None, :, None])))
+    lat = torch.empty((B, C, W), device=DEV)
+    out = torch.empty((B, Ld, W), device=DEV)
+    xd, wd, bd = torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV), torch.from_numpy(b).to(DEV)
+    _lib.check(L.modfx_cnn_head_f32(_vp(xd), _vp(lat), _vp(out), B, H, W, C, Ld, _vp(wd), _vp(bd), _stream()))
+    assert maxdiff(lat.cpu().numpy(), lat_ref) <= 1e-6
+    assert maxdiff(out.cpu().numpy(), out_ref) <= 1e-6
+
+
+def test_body_fp32_on_reference_logmel_small():
+    g = golden("cnn")
+    net, _ = make_net(8192, 64, 7, "fp32")
+    y, lat = net.forward_features(torch.from_numpy(g["small_logmel"]).to(DEV))
+    assert y.shape == (3, 1, 33) and lat.shape == (3, 64, 33)
+    assert maxdiff(y.cpu().numpy(), g["small_y"]) <= 2e-5
+    assert maxdiff(lat.cpu().numpy(), g["small_latent"]) <= 1e-4
+
+
+def test_body_tf32_on_reference_logmel_small():
+    from oracle import oracle
+    g = golden("cnn")
+    net, sd = make_net(8192, 64, 7, "tf32")
+    y, lat = net.forward_features(torch.from_numpy(g["small_logmel"]).to(DEV))
+    assert maxdiff(y.cpu().numpy(), g["small_y"]) <= 3e-3
+    assert maxdiff(lat.cpu().numpy(), g["small_latent"]) <= 1e-2
+    convs, ow, ob = cnn_oracle_args(sd)
+    yo, lo = oracle.spectral_2dcnn_body(g["small_logmel"], convs, ow, ob, CNN_DILATIONS, tf32_from_layer=1)
+    assert maxdiff(y.cpu().numpy(), yo) <= 5e-4
+    assert maxdiff(lat.cpu().numpy(), lo) <= 2e-3
+
+
+@pytest.mark.parametrize("precision,tol_y,tol_lat", [("fp32", 2e-4, 1e-3), ("tf32", 3e-3, 1e-2)])
+def test_end_to_end_small(precision, tol_y, tol_lat):
+    g = golden("cnn")
+    net, _ = make_net(8192, 64, 7, precision, fb=g["small_fb"])
+    y, lat = net(torch.from_numpy(g["small_x"]).to(DEV))
+    assert maxdiff(y.cpu().numpy(), g["small_y"]) <= tol_y
+    assert maxdiff(lat.cpu().numpy(), g["small_latent"]) <= tol_lat
+
+
+def test_training_forward_replays_specaugment_draws():
+    """models.py:201-205: FrequencyMasking then TimeMasking, two draws each from the torch global generator."""
+    g = golden("cnn")
+    net, _ = make_net(8192, 64, 7, "fp32", fb=g["small_fb"])
+    net.train()
+    torch.manual_seed(int(g["train_seed"]))
+    y, lat = net(torch.from_numpy(g["small_x"]).to(DEV))
+    assert maxdiff(y.cpu().numpy(), g["train_y"]) <= 2e-4
+    assert maxdiff(lat.cpu().numpy(), g["train_latent"]) <= 1e-3
+    assert maxdiff(g["train_y"], g["small_y"]) > 1e-3          # the masks did change the result
+
+
+@pytest.mark.parametrize("precision,tol_y,tol_lat", [("fp32", 2e-4, 1e-3), ("tf32", 3e-3, 1e-2)])
+def test_end_to_end_shipped_shape(precision, tol_y, tol_lat):
+    """configs/models/spectral_2dcnn.yml on 2 s clips: (2, 2, 88200) -> (2, 1, 345), (2, 64, 345)."""
+    g = golden("cnn")
+    s0, s1 = [int(s) for s in g["full_x_seeds"]]
+    x = torch.cat([t_white((2, 1, 88200), s0), t_guitar(2, 88200, s1)], dim=1)
+    assert np.array_equal(x.numpy()[..., ::4410], g["full_x_probe"]), "seeded input differs from the golden run"
+    net, _ = make_net(88200, 256, 8, precision)
+    y, lat = net(x.to(DEV))
+    assert y.shape == (2, 1, 345) and lat.shape == (2, 64, 345)
+    assert maxdiff(y.cpu().numpy(), g["full_y"]) <= tol_y
+    assert maxdiff(lat.cpu().numpy(), g["full_latent"]) <= tol_lat
+
+
+def test_batch_independence_and_determinism_tf32():
+    net, _ = make_net(88200, 256, 8, "tf32")
+    x = t_white((5, 2, 88200), 99).to(DEV)
+    y0, l0 = net(x)
+    y1, l1 = net(x)
+    assert torch.equal(y0, y1) and torch.equal(l0, l1)
+    y2, l2 = net(x[2:4])
+    assert torch.equal(y0[2:4], y2) and torch.equal(l0[2:4], l2)
+
+
+def test_unsupported_shapes_fail_loudly():
+    from mod_extraction_b200 import _lib
+    from mod_extraction_b200.models import Spectral2DCNN, _stream, _vp
+    with pytest.raises(NotImplementedError):
+        Spectral2DCNN(in_ch=2, kernel_size=(3, 3), out_channels=[64] * 6, pool_size=(2, 1))
+    L = _lib.lib()
+    t = torch.zeros(16, device=DEV)
+    assert L.modfx_cnn_conv_pool_prelu_f32(_vp(t), _vp(t[8:]), 1, 2, 4, 64, 32, 5, 13, 1, _vp(t), _vp(t), _vp(t), 0,
+                                           _stream()) == -2
+    assert L.modfx_cnn_conv_pool_prelu_f32(_vp(t), _vp(t[8:]), 1, 2, 4, 2, 64, 5, 13, 1, _vp(t), _vp(t), _vp(t), 1,
+                                           _stream()) == -2       # tensor-core path needs Cin = 64

@@ -135,3 +135,41 @@ def test_postproc_oracle_bitwise():
         assert np.array_equal(oracle.smoothen(g["smooth_x"], w), g[f"smooth_y{w}"]), w
     for w in (5, 12):       # torch's tail handling for windows that are not a multiple of 8 is not restated
         assert np.abs(oracle.smoothen(g["smooth_x"], w) - g[f"smooth_y{w}"]).max() <= 2e-7, w
+
+
+def test_cnn_oracle_vs_reference_goldens():
+    """N3: numpy restatement of Spectral2DCNN's body (models.py:183-195,209-214) against the reference's outputs."""
+    from tests.helpers import CNN_DILATIONS, cnn_oracle_args, cnn_weights
+    g = golden("cnn")
+    convs, ow, ob = cnn_oracle_args(cnn_weights(7))
+    y, lat = oracle.spectral_2dcnn_body(g["small_logmel"], convs, ow, ob, CNN_DILATIONS)
+    assert y.shape == g["small_y"].shape == (3, 1, 33)
+    assert np.abs(y - g["small_y"]).max() <= 5e-6
+    assert np.abs(lat - g["small_latent"]).max() <= 2e-5
+    # TF32-rounded operands from layer 2 on (what the tensor-core path computes): within the stated TF32 bars
+    y, lat = oracle.spectral_2dcnn_body(g["small_logmel"], convs, ow, ob, CNN_DILATIONS, tf32_from_layer=1)
+    assert np.abs(y - g["small_y"]).max() <= 3e-3
+    assert np.abs(lat - g["small_latent"]).max() <= 1e-2
+
+
+def test_cnn_shim_keeps_reference_interface():
+    """Same constructor keywords and state-dict keys as models.py:127-195; CPU tensors are refused (no fallback)."""
+    import torch
+    from tests.helpers import CNN_DILATIONS, cnn_weights
+    from mod_extraction_b200.models import Spectral2DCNN, round_to_tf32
+    net = Spectral2DCNN(in_ch=2, n_samples=8192, sr=44100, n_fft=1024, hop_len=256, n_mels=64, kernel_size=(5, 13),
+                        out_channels=[64] * 6, bin_dilations=None, temp_dilations=CNN_DILATIONS, pool_size=(2, 1),
+                        latent_dim=1, freq_mask_amount=0.25, time_mask_amount=0.25, use_ln=True, eps=1e-7)
+    sd = cnn_weights(7)
+    assert sorted(net.state_dict().keys()) == sorted(sd.keys())
+    ref_style = {k: torch.from_numpy(v) for k, v in sd.items()}
+    ref_style["spectrogram.spectrogram.window"] = torch.hann_window(1024)
+    ref_style["spectrogram.mel_scale.fb"] = torch.rand(513, 64)
+    net.load_state_dict(ref_style)                      # a reference checkpoint loads unchanged
+    assert torch.equal(net.spectrogram.fb, ref_style["spectrogram.mel_scale.fb"])
+    assert net.freq_mask_param == 16 and net.time_mask_param == 8
+    with pytest.raises(RuntimeError):
+        net.eval()(torch.zeros(1, 2, 8192))
+    w = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -3.1415927], dtype=torch.float32)
+    assert np.array_equal(round_to_tf32(w).numpy(), oracle.round_tf32(w.numpy()))
+    assert float(round_to_tf32(w)[1]) == 1.0 + 2 ** -10
