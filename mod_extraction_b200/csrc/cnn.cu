@@ -16,6 +16,8 @@ namespace modfx {
 
 int cnn_conv_tf32(const float* x, float* y, int B, int H, int W, int dil_w, const float* weight, const float* bias,
                   const float* prelu, cudaStream_t stream);      // cnn_tc.cu
+int cnn_conv1_tf32(const float* x, float* y, int B, int H, int W, const float* weight, const float* bias,
+                   const float* prelu, cudaStream_t stream);     // cnn_tc.cu (2 input channels, dilation 1)
 
 namespace {
 
@@ -330,7 +332,10 @@ extern "C" int modfx_cnn_conv_pool_prelu_f32(const float* x, float* y, int32_t B
     MODFX_REQUIRE(B <= 65535 && H / 2 <= 65535, "grid too large");
     cudaStream_t st = as_stream(stream);
     if (precision == MODFX_CNN_TF32) {
-        if (Cin != 64) return fail(MODFX_ERR_UNSUPPORTED, "the tensor-core convolution is built for Cin=64 (got %d)", Cin);
+        if (Cin == 2 && dil_w == 1) return cnn_conv1_tf32(x, y, B, H, W, weight, bias, prelu, st);
+        if (Cin != 64)
+            return fail(MODFX_ERR_UNSUPPORTED, "the tensor-core convolution is built for Cin=64, and Cin=2 with dilation 1 (got %d, %d)",
+                        Cin, dil_w);
         return cnn_conv_tf32(x, y, B, H, W, dil_w, weight, bias, prelu, st);
     }
     if (precision != MODFX_CNN_FP32) return fail(MODFX_ERR_INVALID, "precision=%d", precision);

@@ -260,7 +260,8 @@ class Spectral2DCNN(nn.Module):
             for i in range(len(self.out_channels)):
                 conv, act = self.cnn[4 * i + 1], self.cnn[4 * i + 3]
                 w = conv.weight.detach().to(device=device, dtype=torch.float32).permute(2, 3, 0, 1).contiguous()
-                tc = self.precision == "tf32" and w.size(3) == 64
+                # tensor-core layers: 64 input channels, or the 2-channel first layer when it is not dilated
+                tc = self.precision == "tf32" and (w.size(3) == 64 or (w.size(3) == 2 and self.temp_dilations[i] == 1))
                 if tc:
                     w = round_to_tf32(w)
                 packed.append((w, conv.bias.detach().to(device=device, dtype=torch.float32).contiguous(),
@@ -286,7 +287,8 @@ class Spectral2DCNN(nn.Module):
             ws_bytes = max(L.modfx_cnn_layernorm_workspace_bytes(B, C, H, W), L.modfx_cnn_layernorm_workspace_bytes(B, 64, H // 2, W))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             x = torch.empty((B, H, W, C), dtype=torch.float32, device=dev)
-            _lib.check(L.modfx_cnn_layernorm_f32(_vp(logmel), _vp(x), B, C, H, W, 1, self.ln_eps, 0, _vp(ws), _stream()))
+            _lib.check(L.modfx_cnn_layernorm_f32(_vp(logmel), _vp(x), B, C, H, W, 1, self.ln_eps,
+                                                 1 if packed[0][3] == _lib.CNN_TF32 else 0, _vp(ws), _stream()))
             for i, (w, bias, slope, prec) in enumerate(packed):
                 y = torch.empty((B, H // 2, W, 64), dtype=torch.float32, device=dev)
                 _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(x), _vp(y), B, H, W, C, 64, 5, 13, self.temp_dilations[i],

@@ -51,9 +51,11 @@ x = torch.randn(B, 256, W, 2, device=dev)
 w = torch.randn(5, 13, 64, 2, device=dev) * 0.1
 b = torch.zeros(64, device=dev)
 y = torch.empty(B, 128, W, 64, device=dev)
-ms = timed(lambda: _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(x), _vp(y), B, 256, W, 2, 64, 5, 13, 1, _vp(w), _vp(b), _vp(b),
-                                                              0, _stream())))
-print(f"layer 1 (2 -> 64, CUDA cores): {ms:.3f} ms  {2.0 * B * 256 * W * 2 * 64 * 65 / ms / 1e9:.1f} TFLOP/s")
+for code, name in ((0, "CUDA cores"), (1, "tcgen05")):
+    ms = timed(lambda: _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(x), _vp(y), B, 256, W, 2, 64, 5, 13, 1, _vp(w), _vp(b), _vp(b),
+                                                                  code, _stream())))
+    print(f"layer 1 (2 -> 64, {name}): {ms:.3f} ms  {2.0 * B * 256 * W * 2 * 64 * 65 / ms / 1e9:.1f} TFLOP/s  "
+          f"{y.numel() * 4 / ms / 1e6:.0f} GB/s of output")
 ws = torch.empty(L.modfx_cnn_layernorm_workspace_bytes(B, 64, 128, W), dtype=torch.uint8, device=dev)
 ms = timed(lambda: _lib.check(L.modfx_cnn_layernorm_f32(_vp(y), _vp(y), B, 64, 128, W, 0, 1e-5, 1, _vp(ws), _stream())))
 print(f"layer norm of (B, 128, 345, 64): {ms:.3f} ms  {2 * y.numel() * 4 / ms / 1e6:.0f} GB/s (read twice + write once: x1.5)")

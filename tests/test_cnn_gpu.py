@@ -133,6 +133,36 @@ def test_conv_pool_prelu_tcgen05_vs_fp32_kernel_and_oracle(dil, H, W, B):
     assert maxdiff(got, ref) <= 1e-4
 
 
+@pytest.mark.parametrize("H,W,B", [(4, 33, 2), (2, 128, 1), (8, 130, 2), (256, 345, 2), (6, 345, 3)])
+def test_first_layer_tcgen05_vs_fp32_kernel_and_oracle(H, W, B):
+    """The 2-channel first layer on the tensor cores (13 taps folded into K, operand tiles written by the CTA itself)."""
+    from mod_extraction_b200 import _lib
+    from mod_extraction_b200.models import _stream, _vp, round_to_tf32
+    from oracle import oracle
+    L = _lib.lib()
+    rng = np.random.RandomState(200 + H + W)
+    x = rng.standard_normal((B, 2, H, W)).astype(np.float32)
+    w = (rng.standard_normal((64, 2, 5, 13)) / math.sqrt(2 * 65)).astype(np.float32)
+    bias = rng.uniform(-0.2, 0.2, 64).astype(np.float32)
+    slope = rng.uniform(0.05, 0.4, 64).astype(np.float32)
+    xd = round_to_tf32(torch.from_numpy(x).to(DEV).permute(0, 2, 3, 1).contiguous())
+    wd = round_to_tf32(torch.from_numpy(w).to(DEV).permute(2, 3, 0, 1).contiguous())
+    bd, sd = torch.from_numpy(bias).to(DEV), torch.from_numpy(slope).to(DEV)
+    y_tc = torch.full((B, H // 2, W, 64), float("nan"), device=DEV)
+    y_cc = torch.empty((B, H // 2, W, 64), device=DEV)
+    _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(xd), _vp(y_tc), B, H, W, 2, 64, 5, 13, 1, _vp(wd), _vp(bd), _vp(sd),
+                                               _lib.CNN_TF32, _stream()))
+    _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(xd), _vp(y_cc), B, H, W, 2, 64, 5, 13, 1, _vp(wd), _vp(bd), _vp(sd),
+                                               _lib.CNN_FP32, _stream()))
+    torch.cuda.synchronize()
+    got = y_tc.cpu().numpy()
+    assert np.isfinite(got).all(), "tensor-core kernel left outputs unwritten"
+    assert maxdiff(got, y_cc.cpu().numpy()) <= 1e-4
+    if H <= 8:
+        ref = oracle.prelu(oracle.max_pool_h2(oracle.conv2d_same(x, w, bias, 1, tf32=True)), slope).transpose(0, 2, 3, 1)
+        assert maxdiff(got, ref) <= 1e-4
+
+
 def test_head_vs_oracle():
     from mod_extraction_b200 import _lib
     from mod_extraction_b200.models import _stream, _vp
@@ -169,7 +199,7 @@ def test_body_tf32_on_reference_logmel_small():
     assert maxdiff(y.cpu().numpy(), g["small_y"]) <= 3e-3
     assert maxdiff(lat.cpu().numpy(), g["small_latent"]) <= 1e-2
     convs, ow, ob = cnn_oracle_args(sd)
-    yo, lo = oracle.spectral_2dcnn_body(g["small_logmel"], convs, ow, ob, CNN_DILATIONS, tf32_from_layer=1)
+    yo, lo = oracle.spectral_2dcnn_body(g["small_logmel"], convs, ow, ob, CNN_DILATIONS, tf32_from_layer=0)
     assert maxdiff(y.cpu().numpy(), yo) <= 5e-4
     assert maxdiff(lat.cpu().numpy(), lo) <= 2e-3
 
@@ -228,5 +258,5 @@ def test_unsupported_shapes_fail_loudly():
     t = torch.zeros(16, device=DEV)
     assert L.modfx_cnn_conv_pool_prelu_f32(_vp(t), _vp(t[8:]), 1, 2, 4, 64, 32, 5, 13, 1, _vp(t), _vp(t), _vp(t), 0,
                                            _stream()) == -2
-    assert L.modfx_cnn_conv_pool_prelu_f32(_vp(t), _vp(t[8:]), 1, 2, 4, 2, 64, 5, 13, 1, _vp(t), _vp(t), _vp(t), 1,
-                                           _stream()) == -2       # tensor-core path needs Cin = 64
+    assert L.modfx_cnn_conv_pool_prelu_f32(_vp(t), _vp(t[8:]), 1, 2, 4, 2, 64, 5, 13, 2, _vp(t), _vp(t), _vp(t), 1,
+                                           _stream()) == -2       # tensor-core path: Cin = 64, or Cin = 2 undilated
