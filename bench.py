@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=96, help="examples in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extractor", action="store_true")
+    ap.add_argument("--extractor-batch", type=int, default=128, help="clips per forward of the extractor side measurement")
     ap.add_argument("--e2e-chunk", type=int, default=512, help="examples per pipelined chunk of the host-buffer path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -384,6 +386,35 @@ def main():
                        "log-mel mean out, chunks pipelined over copy/compute/copy streams; the (B,2,256,345) log-mel "
                        "tensor stays in HBM where the extractor consumes it"}
 
+    # ---------------- the consumer of the step's log-mel tensor, reported beside the headline, not in it
+    extractor = None
+    if not args.no_extractor:
+        from mod_extraction_b200.models import Spectral2DCNN
+        net = Spectral2DCNN(in_ch=2, n_samples=N, sr=SR, out_channels=[64] * 6, temp_dilations=[1, 1, 2, 4, 8, 16],
+                            pool_size=(2, 1), precision="tf32").to(dev).eval()
+        Bx = min(args.extractor_batch, B)
+        feats = logmel[:Bx]
+        for _ in range(2):
+            net.forward_features(feats)
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        x0.record()
+        for _ in range(reps):
+            out_x, _ = net.forward_features(feats)
+        x1.record()
+        torch.cuda.synchronize()
+        ms_x = x0.elapsed_time(x1) / reps
+        flops = 2.0 * 65 * 64 * 345 * (256 * 2 + 64 * (128 + 64 + 32 + 16 + 8)) * Bx      # the six convolutions
+        tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+        extractor = {"what": "Spectral2DCNN body on the log-mel of this step (6 x {layer norm, 5x13 conv + pool + PReLU on "
+                             "tcgen05 TF32}, head), random weights", "batch": Bx, "ms": ms_x,
+                     "audio_s_per_s": Bx * (N / SR) / (ms_x * 1e-3), "conv_tflops": flops / (ms_x * 1e-3) / 1e12,
+                     "tf32_peak_tflops": tf32_peak,
+                     "tf32_peak_source": "half of MEASURED_PEAKS.json bf16_tflops (no TF32 figure is measured by the driver)",
+                     "frac_of_tf32_peak": flops / (ms_x * 1e-3) / 1e12 / tf32_peak, "gpu_launches_per_forward": 19,
+                     "output_mean": float(out_x.mean().item())}
+        del net
+
     # ---------------- final gather of per-rank metrics (the only collective, outside the timed region)
     checksum = float(wet.double().abs().mean().item())
     gather_ms = None
@@ -416,7 +447,7 @@ def main():
                        "parallelism": f"batch-sharded x{world}, no collective while rendering"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * 10,      # per step: flanger 1 + chorus 1 + phaser 4 + log-mel 4
             "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "lfo_generation_s": lfo_gen_s, "metrics_gather_ms": gather_ms,
+            "cpu_baseline": cpu_baseline, "extractor": extractor, "lfo_generation_s": lfo_gen_s, "metrics_gather_ms": gather_ms,
             "wet_abs_mean": checksum,
         }
         print(json.dumps(line), flush=True)

@@ -17,7 +17,9 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "smsp__inst_executed
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__average_warp_latency_per_inst_issued.ratio"]
+        "smsp__average_warp_latency_per_inst_issued.ratio",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
 
 
 def run(args):
