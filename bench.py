@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extractor", action="store_true")
+    ap.add_argument("--gather-rendered", action="store_true",
+                    help="N > 1: also time the optional all-gather of the rendered wet batch (outside the timed region)")
     ap.add_argument("--extractor-batch", type=int, default=128, help="clips per forward of the extractor side measurement")
     ap.add_argument("--e2e-chunk", type=int, default=512, help="examples per pipelined chunk of the host-buffer path")
     args = ap.parse_args()
@@ -428,6 +430,26 @@ def main():
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1)
         checksum = float(out.mean().item())
+    rendered_gather = None
+    if world > 1 and args.gather_rendered:
+        from mod_extraction_b200.sharding import all_gather_rendered
+        if extractor is not None:
+            torch.cuda.empty_cache()
+        all_gather_rendered(wet[:8], 8 * world)                      # NCCL warm-up
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        full = all_gather_rendered(wet, world * B)
+        g1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nbytes = full.numel() * 4
+        rendered_gather = {"ms": float(t.item()), "bytes_gathered_per_rank": nbytes,
+                           "inbound_gbs_per_rank": nbytes * (world - 1) / world / (float(t.item()) * 1e-3) / 1e9,
+                           "note": "sharding.all_gather_rendered(wet): every rank ends with the whole (world*B, 1, N) batch; "
+                                   "optional, outside the timed region (SURVEY H7)"}
+        del full
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -448,6 +470,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * 10,      # per step: flanger 1 + chorus 1 + phaser 4 + log-mel 4
             "roofline": roofline,
             "cpu_baseline": cpu_baseline, "extractor": extractor, "lfo_generation_s": lfo_gen_s, "metrics_gather_ms": gather_ms,
+            "rendered_gather": rendered_gather,
             "wet_abs_mean": checksum,
         }
         print(json.dumps(line), flush=True)

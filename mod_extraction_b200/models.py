@@ -197,7 +197,7 @@ class Spectral2DCNN(nn.Module):
                  out_channels: Optional[List[int]] = None, bin_dilations: Optional[List[int]] = None,
                  temp_dilations: Optional[List[int]] = None, pool_size: Tuple[int, int] = (3, 1),
                  latent_dim: int = 1, freq_mask_amount: float = 0.0, time_mask_amount: float = 0.0,
-                 use_ln: bool = True, eps: float = 1e-7, precision: str = "tf32") -> None:
+                 use_ln: bool = True, eps: float = 1e-7, precision: str = "tf32", max_chunk: int = 256) -> None:
         super().__init__()
         assert pool_size[1] == 1
         if out_channels is None:
@@ -219,6 +219,7 @@ class Spectral2DCNN(nn.Module):
         self.freq_mask_amount, self.time_mask_amount, self.use_ln, self.eps = freq_mask_amount, time_mask_amount, use_ln, eps
         self.out_channels, self.bin_dilations, self.temp_dilations = list(out_channels), list(bin_dilations), list(temp_dilations)
         self.precision = precision
+        self.max_chunk = max_chunk                # examples per pass: the first layer's output is 11.3 MB per example
         self.ln_eps = 1e-5                        # nn.LayerNorm default (models.py:186)
 
         self.spectrogram = LogMelSpectrogram(sample_rate=int(sr), n_fft=n_fft, hop_length=hop_len, n_mels=n_mels, eps=eps)
@@ -282,6 +283,9 @@ class Spectral2DCNN(nn.Module):
         logmel = logmel.detach().float().contiguous()
         B, C, H, W = logmel.shape
         assert C == self.in_ch and H == self.n_mels
+        if B > self.max_chunk:                    # examples are independent: bound the activation memory
+            outs = [self.forward_features(logmel[i:i + self.max_chunk]) for i in range(0, B, self.max_chunk)]
+            return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
         packed, w_out, b_out = self._pack(dev)
         with torch.cuda.device(dev):
             ws_bytes = max(L.modfx_cnn_layernorm_workspace_bytes(B, C, H, W), L.modfx_cnn_layernorm_workspace_bytes(B, 64, H // 2, W))

@@ -247,6 +247,9 @@ def test_batch_independence_and_determinism_tf32():
     assert torch.equal(y0, y1) and torch.equal(l0, l1)
     y2, l2 = net(x[2:4])
     assert torch.equal(y0[2:4], y2) and torch.equal(l0[2:4], l2)
+    net.max_chunk = 2                                   # chunked passes give the same bits
+    y3, l3 = net(x)
+    assert torch.equal(y0, y3) and torch.equal(l0, l3)
 
 
 def test_unsupported_shapes_fail_loudly():
