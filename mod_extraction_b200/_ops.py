@@ -289,3 +289,56 @@ def stretch_sections(x: Tensor, sec_off, in_start, in_len, new_len, out_start) -
         _lib.check(_lib.lib().modfx_stretch_sections_f32(_ptr(x), _ptr(out), x.size(0), x.size(1),
                                                          *[_ptr(t) for t in ts], _stream()))
     return out
+
+
+# ---- LFO-net body, channels-last activations -----------------------------------------------
+def cnn_layernorm(x: Tensor, x_is_nchw: bool = False, eps: float = 1e-5, round_tf32: bool = False,
+                  out: Optional[Tensor] = None) -> Tensor:
+    """nn.LayerNorm([H, W], elementwise_affine=False) per (b, c) (models.py:186).  x (B, C, H, W) when
+    `x_is_nchw` else (B, H, W, C); returns (B, H, W, C) (in place when `out is x` and x is channels-last)."""
+    _require_cuda(x, "x")
+    assert x.ndim == 4
+    x = x.contiguous()
+    B, C, H, W = x.shape if x_is_nchw else (x.size(0), x.size(3), x.size(1), x.size(2))
+    if out is None:
+        out = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+    L = _lib.lib()
+    ws = torch.empty(max(int(L.modfx_cnn_layernorm_workspace_bytes(B, C, H, W)), 16), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.modfx_cnn_layernorm_f32(_ptr(x), _ptr(out), B, C, H, W, 1 if x_is_nchw else 0, float(eps),
+                                             1 if round_tf32 else 0, _ptr(ws), _stream()))
+        ws.record_stream(torch.cuda.current_stream())
+    return out
+
+
+def cnn_conv_pool_prelu(x: Tensor, weight: Tensor, bias: Tensor, slope: Tensor, dil_w: int = 1, tf32: bool = True) -> Tensor:
+    """Conv2d(Cin, 64, (5, 13), dilation=(1, dil_w), padding="same") -> MaxPool2d((2, 1)) -> PReLU (models.py:187-189).
+    x (B, H, W, Cin) channels-last; weight (5, 13, 64, Cin); returns (B, H/2, W, 64).  tf32: tcgen05 tensor cores."""
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias"), (slope, "slope")):
+        _require_cuda(t, n)
+    assert x.ndim == 4 and weight.ndim == 4 and weight.size(3) == x.size(3)
+    x, weight, bias, slope = x.contiguous(), weight.contiguous(), bias.contiguous(), slope.contiguous()
+    B, H, W, Cin = x.shape
+    KH, KW, Cout, _ = weight.shape
+    y = torch.empty((B, H // 2, W, Cout), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().modfx_cnn_conv_pool_prelu_f32(
+            _ptr(x), _ptr(y), B, H, W, Cin, Cout, KH, KW, int(dil_w), _ptr(weight), _ptr(bias), _ptr(slope),
+            _lib.CNN_TF32 if tf32 else _lib.CNN_FP32, _stream()))
+    return y
+
+
+def cnn_head(x: Tensor, weight: Tensor, bias: Tensor):
+    """tr.mean(x, dim=-2) -> Conv1d(C, L, 1) -> sigmoid (models.py:210-214).  x (B, H, W, C) channels-last,
+    weight (L, C); returns (output (B, L, W), latent (B, C, W))."""
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias")):
+        _require_cuda(t, n)
+    x, weight, bias = x.contiguous(), weight.contiguous(), bias.contiguous()
+    B, H, W, C = x.shape
+    Ld = weight.size(0)
+    latent = torch.empty((B, C, W), device=x.device, dtype=torch.float32)
+    out = torch.empty((B, Ld, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().modfx_cnn_head_f32(_ptr(x), _ptr(latent), _ptr(out), B, H, W, C, Ld, _ptr(weight), _ptr(bias),
+                                                 _stream()))
+    return out, latent

@@ -8,8 +8,10 @@ libmodfx.so of ``_ops.py``; registering them costs nothing when the ops are not 
     torch.ops.modfx.flanger_chorus(x, mod_lo, feedback, min_delay_width, width, depth, mix, m_min, m_lfo)
     torch.ops.modfx.interp_linear(x, n, align_corners)
     torch.ops.modfx.lfo(freq, phase, shape, exp, n, sr)
-    torch.ops.modfx.logmel(x, window, fb_start, fb_count, fb_weight, fb_taps, hop, eps, apply_log)
     torch.ops.modfx.phaser(x, rate_hz, depth, centre_hz, feedback, mix, sr, block)
+    torch.ops.modfx.cnn_layernorm(x, x_is_nchw, eps, round_tf32)               # -> channels-last (B, H, W, C)
+    torch.ops.modfx.cnn_conv_pool_prelu(x, weight, bias, slope, dil_w, tf32)    # tcgen05 when tf32
+    torch.ops.modfx.cnn_head(x, weight, bias)                                   # -> (output, latent)
 """
 from __future__ import annotations
 
@@ -26,6 +28,9 @@ _lib.define("interp_linear(Tensor x, int n, bool align_corners) -> Tensor")
 _lib.define("lfo(Tensor freq, Tensor phase, Tensor shape, Tensor exp, int n, float sr) -> Tensor")
 _lib.define("phaser(Tensor x, Tensor rate_hz, Tensor depth, Tensor centre_hz, Tensor feedback, Tensor mix, "
             "float sr, int block) -> Tensor")
+_lib.define("cnn_layernorm(Tensor x, bool x_is_nchw, float eps, bool round_tf32) -> Tensor")
+_lib.define("cnn_conv_pool_prelu(Tensor x, Tensor weight, Tensor bias, Tensor slope, int dil_w, bool tf32) -> Tensor")
+_lib.define("cnn_head(Tensor x, Tensor weight, Tensor bias) -> (Tensor, Tensor)")
 
 
 def _flanger_chorus(x: Tensor, mod: Tensor, feedback: Tensor, min_delay_width: Tensor, width: Tensor, depth: Tensor,
@@ -52,3 +57,7 @@ _impl.impl("flanger_chorus", _flanger_chorus)
 _impl.impl("interp_linear", _interp_linear)
 _impl.impl("lfo", _lfo)
 _impl.impl("phaser", _phaser)
+_impl.impl("cnn_layernorm", lambda x, x_is_nchw, eps, round_tf32: _ops.cnn_layernorm(x, x_is_nchw, eps, round_tf32))
+_impl.impl("cnn_conv_pool_prelu", lambda x, weight, bias, slope, dil_w, tf32: _ops.cnn_conv_pool_prelu(x, weight, bias, slope,
+                                                                                                      dil_w, tf32))
+_impl.impl("cnn_head", lambda x, weight, bias: _ops.cnn_head(x, weight, bias))

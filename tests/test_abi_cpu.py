@@ -72,5 +72,8 @@ def test_torch_ops_registered_cuda_only():
     import torch
     import mod_extraction_b200._torch_ops  # noqa: F401
     assert hasattr(torch.ops.modfx, "flanger_chorus") and hasattr(torch.ops.modfx, "phaser")
+    assert hasattr(torch.ops.modfx, "cnn_conv_pool_prelu") and hasattr(torch.ops.modfx, "cnn_head")
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.modfx.cnn_layernorm(torch.zeros(1, 2, 4, 4), True, 1e-5, False)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.modfx.interp_linear(torch.zeros(2, 8), 16, True)

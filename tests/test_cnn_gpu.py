@@ -263,3 +263,42 @@ def test_unsupported_shapes_fail_loudly():
                                            _stream()) == -2
     assert L.modfx_cnn_conv_pool_prelu_f32(_vp(t), _vp(t[8:]), 1, 2, 4, 2, 64, 5, 13, 2, _vp(t), _vp(t), _vp(t), 1,
                                            _stream()) == -2       # tensor-core path: Cin = 64, or Cin = 2 undilated
+
+
+def test_torch_ops_match_module_path():
+    """torch.ops.modfx.cnn_* (CUDA dispatch key only) give the bits of Spectral2DCNN.forward_features."""
+    import mod_extraction_b200._torch_ops  # noqa: F401
+    from mod_extraction_b200.models import round_to_tf32
+    g = golden("cnn")
+    net, sd = make_net(8192, 64, 7, "tf32")
+    lm = torch.from_numpy(g["small_logmel"]).to(DEV)
+    y_ref, lat_ref = net.forward_features(lm)
+    x = torch.ops.modfx.cnn_layernorm(lm, True, 1e-5, True)
+    for i in range(6):
+        w = round_to_tf32(torch.from_numpy(sd[f"cnn.{4 * i + 1}.weight"]).to(DEV).permute(2, 3, 0, 1).contiguous())
+        b = torch.from_numpy(sd[f"cnn.{4 * i + 1}.bias"]).to(DEV)
+        a = torch.from_numpy(sd[f"cnn.{4 * i + 3}.weight"]).to(DEV)
+        x = torch.ops.modfx.cnn_conv_pool_prelu(x, w, b, a, CNN_DILATIONS[i], True)
+        if i < 5:
+            x = torch.ops.modfx.cnn_layernorm(x, False, 1e-5, True)
+    y, lat = torch.ops.modfx.cnn_head(x, torch.from_numpy(sd["output.weight"][:, :, 0]).to(DEV),
+                                      torch.from_numpy(sd["output.bias"]).to(DEV))
+    assert torch.equal(y, y_ref) and torch.equal(lat, lat_ref)
+
+
+def test_dry_audio_to_extracted_lfo_on_the_gpu():
+    """The whole chain a user of the reference runs at eval time, device-resident: render (flanger, control-rate LFO)
+    -> log-mel of cat[dry, wet] -> CNN -> smoothing / corner stretching of the extracted LFO (lightning.py:106-127)."""
+    from mod_extraction_b200 import fx, modulations
+    B, N = 4, 88200
+    dry = t_guitar(B, N, 61).to(DEV)
+    mod_lo = modulations.make_mod_signal_batch(882, 441.0, torch.tensor([0.7, 1.1, 1.9, 2.6]), torch.zeros(B), ["tri", "cos", "rect_cos", "saw"])
+    fl = fx.MonoFlangerChorusModule(B, 1, N, SR, 1.0, 10.0)
+    wet = fl.forward_control_rate(dry, mod_lo, 0.4, 0.5, 0.8, 1.0, 1.0)
+    net, _ = make_net(N, 256, 8, "tf32")
+    out, latent = net(torch.cat([dry, wet], dim=1))
+    assert out.shape == (B, 1, 345) and latent.shape == (B, 64, 345) and bool(torch.isfinite(out).all())
+    assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    sm = modulations.smoothen(out.squeeze(1), 8)
+    st = modulations.stretch_corners(out.squeeze(1), max_n_corners=16, smooth_n_frames=8)
+    assert sm.shape == (B, 338) and st.is_cuda and bool(torch.isfinite(st[~torch.isnan(st)]).all())
