@@ -6,9 +6,9 @@ examples are rendered by ``MonoFlangerChorusModule`` from a control-rate LFO (da
 the phaser examples by pedalboard (datasets.py:455-482), and ``Spectral2DCNN.forward`` takes the log-mel
 of ``cat([dry, wet], dim=1)`` (lightning.py:106, models.py:199-208).
 
-Here one call renders the whole interleaved batch on the GPU: three effect launches on three streams
-(examples are selected through index lists, nothing is gathered or copied), and the log-mel kernel
-runs on a fourth stream -- the dry half at once, each wet group as soon as its effect has finished --
+Here one call renders the whole interleaved batch on the GPU: three chains "effect -> log-mel of its wet rows" on
+three high-priority streams (examples are selected through index lists, nothing is gathered or copied) and the
+log-mel of the dry half, which depends on nothing, on a low-priority fourth stream that fills the gaps -- all
 writing straight into the (B, 2, n_mels, n_frames) tensor the extractor consumes.
 """
 from __future__ import annotations
@@ -42,7 +42,10 @@ class InterwovenRenderer:
         self.n_frames = self.front.n_frames(n_samples)
         self.phaser_buffer_size = phaser_buffer_size
         self.concurrent = concurrent
-        self._streams = [torch.cuda.Stream(device=self.device) for _ in range(4)] if concurrent else None
+        # three effect chains (effect -> log-mel of its wet rows) on high-priority streams, the dry log-mel (which
+        # depends on nothing) on a low-priority one: the hardware fills the gaps of the chains with it
+        self._streams = ([torch.cuda.Stream(device=self.device, priority=-1) for _ in range(3)] +
+                         [torch.cuda.Stream(device=self.device, priority=0)]) if concurrent else None
         self._idx_cache: Dict[int, Tuple[Tensor, ...]] = {}
 
     # ------------------------------------------------------------------ helpers
@@ -169,25 +172,22 @@ class InterwovenRenderer:
             return wet, logmel
 
         cur = torch.cuda.current_stream(self.device)
-        s_fl, s_ch, s_ph, s_lm = self._streams
+        s_fl, s_ch, s_ph, s_dry = self._streams
         start = torch.cuda.Event()
         start.record(cur)
-        done = []
-        for s, fn in ((s_fl, effects_fl), (s_ch, effects_ch), (s_ph, effects_ph)):
+        for s, fn, rows in ((s_fl, effects_fl, i_fl), (s_ch, effects_ch, i_ch), (s_ph, effects_ph, i_ph)):
             s.wait_event(start)
             with torch.cuda.stream(s):
                 fn()
+                mel(wet2, lm_wet, rows)                   # same stream: starts when its own effect has finished
                 ev = torch.cuda.Event()
                 ev.record(s)
-                done.append(ev)
-        s_lm.wait_event(start)
-        with torch.cuda.stream(s_lm):
-            mel(dry2, lm_dry, None)                       # needs no effect: starts immediately
-            for ev, rows in ((done[1], i_ch), (done[2], i_ph), (done[0], i_fl)):   # flanger has the longest tail
-                s_lm.wait_event(ev)
-                mel(wet2, lm_wet, rows)
+            cur.wait_event(ev)
+        s_dry.wait_event(start)
+        with torch.cuda.stream(s_dry):
+            mel(dry2, lm_dry, None)                       # needs no effect: background work for the whole step
             fin = torch.cuda.Event()
-            fin.record(s_lm)
+            fin.record(s_dry)
         cur.wait_event(fin)
         for t in (dry, mod_lo, wet, logmel, *fc_args, *ph_args):
             if isinstance(t, Tensor) and t.is_cuda:
