@@ -219,7 +219,9 @@ int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, c
  *                             (biased variance).  x is (B, C, H, W) when x_is_nchw (the log-mel tensor
  *                             the front end writes) else (B, H, W, C); y is always (B, H, W, C) and may
  *                             alias x when both are channels-last.  round_tf32 = 1 rounds y to TF32
- *                             (round-to-nearest), the operand format of the tensor-core convolution.
+ *                             (round-to-nearest), the operand format of the tensor-core convolution;
+ *                             round_tf32 = 2 writes the error-compensated split instead: y holds TWO planes of
+ *                             B*H*W*C floats, hi = tf32(v) and lo = tf32(v - hi) (channels-last input, y != x).
  *                             workspace: modfx_cnn_layernorm_workspace_bytes(B, C, H, W) bytes.
  *   modfx_cnn_conv_pool_prelu_f32
  *                             replaces Conv2d(Cin, Cout, (KH, KW), dilation=(1, dil_w), padding="same")
@@ -232,6 +234,14 @@ int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, c
  *                             operands / float32 accumulation (Cin == 64; what cuDNN does for the
  *                             reference on a GPU, torch.backends.cudnn.allow_tf32 defaults to True).
  *                             Built: KH = 5, KW = 13, Cout = 64, H even.
+ *   modfx_cnn_conv_pool_prelu_tf32x3_f32
+ *                             the same layer (Cin = Cout = 64) in error-compensated TF32 on the tensor cores:
+ *                             operands split as hi + lo (modfx_cnn_layernorm_f32 with round_tf32 = 2 for the
+ *                             activations; the caller splits the weights the same way), three MMA passes
+ *                             hi*hi + hi*lo + lo*hi into one accumulator, a third of the TF32 rate.  The operand
+ *                             rounding error is gone (the dropped lo*lo term is ~2^-22 relative); what remains is
+ *                             the tensor pipe's truncating accumulator: 2e-4 per layer where plain TF32 has
+ *                             1e-3, and float32-grade results through the whole network.
  *   modfx_cnn_head_f32        replaces tr.mean(x, dim=-2), Conv1d(C, L, 1) and tr.sigmoid,
  *                             models.py:210-214: x (B, H, W, C) -> latent (B, C, W), out (B, L, W).
  *                             weight (L, C), bias (L,).
@@ -248,6 +258,9 @@ int modfx_cnn_conv_pool_prelu_f32(const float* x, float* y, int32_t B, int32_t H
                                   int32_t Cout, int32_t KH, int32_t KW, int32_t dil_w,
                                   const float* weight, const float* bias, const float* prelu,
                                   int32_t precision, void* stream);
+int modfx_cnn_conv_pool_prelu_tf32x3_f32(const float* x_hi, const float* x_lo, float* y, int32_t B, int32_t H,
+                                         int32_t W, int32_t dil_w, const float* w_hi, const float* w_lo,
+                                         const float* bias, const float* prelu, void* stream);
 int modfx_cnn_head_f32(const float* x, float* latent, float* out, int32_t B, int32_t H, int32_t W, int32_t C,
                        int32_t L, const float* weight, const float* bias, void* stream);
 

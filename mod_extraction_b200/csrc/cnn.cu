@@ -14,8 +14,8 @@
 
 namespace modfx {
 
-int cnn_conv_tf32(const float* x, float* y, int B, int H, int W, int dil_w, const float* weight, const float* bias,
-                  const float* prelu, cudaStream_t stream);      // cnn_tc.cu
+int cnn_conv_tf32(const float* x, const float* x_lo, float* y, int B, int H, int W, int dil_w, const float* weight,
+                  const float* w_lo, const float* bias, const float* prelu, cudaStream_t stream);      // cnn_tc.cu
 int cnn_conv1_tf32(const float* x, float* y, int B, int H, int W, const float* weight, const float* bias,
                    const float* prelu, cudaStream_t stream);     // cnn_tc.cu (2 input channels, dilation 1)
 
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_stats_kernel(const float* __res
 template <bool kNchw>
 __global__ void __launch_bounds__(kLnThreads) ln_apply_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                               const double* __restrict__ part, int64_t P, int C,
-                                                              int chunks, float eps, int round) {
+                                                              int chunks, float eps, int round, int64_t lo_plane) {
     extern __shared__ float s_stat[];       // [C] mean, [C] rstd
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.y;
@@ -107,6 +107,13 @@ __global__ void __launch_bounds__(kLnThreads) ln_apply_kernel(const float* __res
             v.y = (v.y - s_stat[c + 1]) * s_stat[C + c + 1];
             v.z = (v.z - s_stat[c + 2]) * s_stat[C + c + 2];
             v.w = (v.w - s_stat[c + 3]) * s_stat[C + c + 3];
+            if (round == 2) {       // error-compensated TF32: hi plane here, lo = tf32(v - hi) one plane further
+                const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+                *reinterpret_cast<float4*>(yb + e) = h;
+                *reinterpret_cast<float4*>(yb + lo_plane + e) =
+                    make_float4(round_tf32(v.x - h.x), round_tf32(v.y - h.y), round_tf32(v.z - h.z), round_tf32(v.w - h.w));
+                continue;
+            }
             if (round) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
             *reinterpret_cast<float4*>(yb + e) = v;
         }
@@ -280,6 +287,9 @@ extern "C" int modfx_cnn_layernorm_f32(const float* x, float* y, int32_t B, int3
     MODFX_REQUIRE(x && y && workspace, "NULL pointer");
     MODFX_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
     MODFX_REQUIRE(!(x_is_nchw && x == y), "in-place needs a channels-last input");
+    MODFX_REQUIRE(round_tf32 >= 0 && round_tf32 <= 2, "round_tf32=%d", round_tf32);
+    if (round_tf32 == 2 && (x_is_nchw || (C & 3) || x == y))
+        return fail(MODFX_ERR_UNSUPPORTED, "the hi/lo split needs a channels-last input, C %% 4 == 0 and y != x");
     if (kLnThreads % C != 0 && !x_is_nchw)
         return fail(MODFX_ERR_UNSUPPORTED, "C=%d: the channel count must divide %d", C, kLnThreads);
     if (C > 1024) return fail(MODFX_ERR_UNSUPPORTED, "C=%d too large", C);
@@ -294,11 +304,12 @@ extern "C" int modfx_cnn_layernorm_f32(const float* x, float* y, int32_t B, int3
         const int chunks = ln_chunks(P);
         ln_stats_kernel<<<dim3(chunks, B * C), kLnThreads, 0, st>>>(x, part, P, 1, chunks);
         ln_apply_kernel<true><<<dim3(ln_chunks(P * C), B), kLnThreads, smem, st>>>(x, y, part, P, C, chunks, eps,
-                                                                                   round_tf32);
+                                                                                   round_tf32, 0);
     } else {
         const int chunks = ln_chunks(P * C);
         ln_stats_kernel<<<dim3(chunks, B), kLnThreads, 0, st>>>(x, part, P * C, C, chunks);
-        ln_apply_kernel<false><<<dim3(chunks, B), kLnThreads, smem, st>>>(x, y, part, P, C, chunks, eps, round_tf32);
+        ln_apply_kernel<false><<<dim3(chunks, B), kLnThreads, smem, st>>>(x, y, part, P, C, chunks, eps, round_tf32,
+                                                                          (int64_t)B * P * C);
     }
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
@@ -336,12 +347,25 @@ extern "C" int modfx_cnn_conv_pool_prelu_f32(const float* x, float* y, int32_t B
         if (Cin != 64)
             return fail(MODFX_ERR_UNSUPPORTED, "the tensor-core convolution is built for Cin=64, and Cin=2 with dilation 1 (got %d, %d)",
                         Cin, dil_w);
-        return cnn_conv_tf32(x, y, B, H, W, dil_w, weight, bias, prelu, st);
+        return cnn_conv_tf32(x, nullptr, y, B, H, W, dil_w, weight, nullptr, bias, prelu, st);
     }
     if (precision != MODFX_CNN_FP32) return fail(MODFX_ERR_INVALID, "precision=%d", precision);
     if (Cin == 2) return launch_conv_fp32<2, 2>(x, y, B, H, W, dil_w, weight, bias, prelu, st);
     if (Cin == 64) return launch_conv_fp32<64, 8>(x, y, B, H, W, dil_w, weight, bias, prelu, st);
     return fail(MODFX_ERR_UNSUPPORTED, "Cin=%d (2 and 64 are built)", Cin);
+}
+
+extern "C" int modfx_cnn_conv_pool_prelu_tf32x3_f32(const float* x_hi, const float* x_lo, float* y, int32_t B, int32_t H,
+                                                    int32_t W, int32_t dil_w, const float* w_hi, const float* w_lo,
+                                                    const float* bias, const float* prelu, void* stream) {
+    MODFX_REQUIRE(x_hi && x_lo && y && w_hi && w_lo && bias && prelu, "NULL pointer");
+    MODFX_REQUIRE(B >= 0 && H >= 2 && W >= 1, "bad shape B=%d H=%d W=%d", B, H, W);
+    MODFX_REQUIRE(x_hi != y && x_lo != y, "x and y must not alias");
+    if ((H & 1) || dil_w < 1 || dil_w > kMaxDil)
+        return fail(MODFX_ERR_UNSUPPORTED, "H=%d must be even and the time dilation %d in [1, %d]", H, dil_w, kMaxDil);
+    if (B == 0) return MODFX_OK;
+    MODFX_REQUIRE(B <= 65535 && H / 2 <= 65535, "grid too large");
+    return cnn_conv_tf32(x_hi, x_lo, y, B, H, W, dil_w, w_hi, w_lo, bias, prelu, as_stream(stream));
 }
 
 extern "C" int modfx_cnn_head_f32(const float* x, float* latent, float* out, int32_t B, int32_t H, int32_t W,

@@ -145,8 +145,17 @@ struct RowPlan {
     }
 };
 
-__global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x,
-                                                                const __grid_constant__ CUtensorMap tm_w,
+// n_pass = 1: plain TF32.  n_pass = 3: error-compensated TF32 ("3xTF32"): activations and weights arrive split as
+// hi + lo (hi = the value rounded to TF32, lo = the rounded remainder) and the tap loop runs three times into the same
+// accumulators -- hi*hi, hi*lo, lo*hi (lo*lo is below float32 resolution) -- at a third of the TF32 rate.  That removes
+// the operand rounding; the residual (2e-4 per layer against 1e-3 for plain TF32) is the tensor pipe's accumulator, which
+// truncates rather than rounds.  Through the whole network the mode meets the float32 parity bars.
+struct ConvMaps {
+    CUtensorMap x[2];       // activations: hi, lo
+    CUtensorMap w[2];       // weights: hi, lo
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_constant__ ConvMaps tm, int n_pass,
                                                                 float* __restrict__ y, int H, int W, int dil,
                                                                 const float* __restrict__ bias,
                                                                 const float* __restrict__ prelu) {
@@ -199,7 +208,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         // ===== A producer (whole warp walks the loop, one elected lane issues): a 128-frame x 64-channel box per
         // (kw, live input row) =====
         int it = 0;
-        for (int kw = 0; kw < kKW; ++kw) {
+        for (int v = 0; v < n_pass * kKW; ++v) {                     // v = pass * 13 + kw
+            const int pass = v / kKW, kw = v - pass * kKW;
+            const CUtensorMap* tmx = &tm.x[pass == 2 ? 1 : 0];      // passes: hi*hi, hi*lo, lo*hi
             const int wx = w0 + (kw - kKW / 2) * dil;
             for (int r = 0; r < kInRows; ++r) {
                 if (!plan.row_live(r)) continue;
@@ -209,8 +220,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
                     const uint32_t full = bar_afull + 8 * s;
                     const uint32_t st = a_base + s * kStageA;
                     mbar_expect_tx(full, kStageA);
-                    tma_load_4d(st, &tm_x, full, 0, wx, plan.h0 - kKH / 2 + r, b);
-                    tma_load_4d(st + kPanelA, &tm_x, full, 32, wx, plan.h0 - kKH / 2 + r, b);
+                    tma_load_4d(st, tmx, full, 0, wx, plan.h0 - kKH / 2 + r, b);
+                    tma_load_4d(st + kPanelA, tmx, full, 32, wx, plan.h0 - kKH / 2 + r, b);
                 }
                 __syncwarp();
                 ++it;
@@ -218,16 +229,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         }
     } else if (warp == 2) {
         // ===== B producer: the 5 kernel rows of one kw, slot j = 4 - kh, refilled as soon as the MMAs release it =====
-        for (int kw = 0; kw < kKW; ++kw) {
+        for (int v = 0; v < n_pass * kKW; ++v) {
+            const int pass = v / kKW, kw = v - pass * kKW;
+            const CUtensorMap* tmw = &tm.w[pass == 1 ? 1 : 0];
             for (int kh = 0; kh < kKH; ++kh) {
                 if (plan.first_use(kh) > plan.last_use(kh)) continue;
                 const int j = kKH - 1 - kh;
-                mbar_wait(bar_bempty + 8 * j, ((uint32_t)kw & 1u) ^ 1u);
+                mbar_wait(bar_bempty + 8 * j, ((uint32_t)v & 1u) ^ 1u);
                 if (elect_one()) {
                     const uint32_t full = bar_bfull + 8 * j;
                     mbar_expect_tx(full, 2 * kTileB);
-                    tma_load_3d(b_base + j * kTileB, &tm_w, full, 0, 0, kh * kKW + kw);
-                    tma_load_3d(b_base + kPanelB + j * kTileB, &tm_w, full, 32, 0, kh * kKW + kw);
+                    tma_load_3d(b_base + j * kTileB, tmw, full, 0, 0, kh * kKW + kw);
+                    tma_load_3d(b_base + kPanelB + j * kTileB, tmw, full, 32, 0, kh * kKW + kw);
                 }
                 __syncwarp();
             }
@@ -264,9 +277,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         }
         int it = 0;
 #pragma unroll 1
-        for (int kw = 0; kw < kKW; ++kw) {
-            const uint32_t b_par = (uint32_t)kw & 1u;
-            uint32_t started = (kw == 0) ? 0u : 0xFFu;             // accumulators that hold a partial sum
+        for (int v = 0; v < n_pass * kKW; ++v) {                     // v = pass * 13 + kw: the weight ring turns once per v
+            const uint32_t b_par = (uint32_t)v & 1u;
+            uint32_t started = (v == 0) ? 0u : 0xFFu;              // accumulators that hold a partial sum
 #pragma unroll
             for (int r = 0; r < kInRows; ++r) {
                 if (!live[r]) continue;
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
                 if (run_n[r] > 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_lo = umma_desc_lo(a_base) + s * (kStageA >> 4);
-                    // at kw = 0 a fresh accumulator overwrites while its neighbours already add: split the run there
+                    // at the very first tap a fresh accumulator overwrites while its neighbours already add: split the run there
                     int a = run_a[r];
                     int left = run_n[r];
                     while (left > 0) {
@@ -559,21 +572,15 @@ EncodeTiledFn encode_tiled() {
 
 }  // namespace
 
-int cnn_conv_tf32(const float* x, float* y, int B, int H, int W, int dil, const float* weight, const float* bias,
-                  const float* prelu, cudaStream_t stream) {
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return fail(MODFX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    MODFX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(y) & 15) == 0,
-                  "x, y and weight must be 16-byte aligned");
-    CUtensorMap tm_x, tm_w;
+static int make_maps(EncodeTiledFn enc, CUtensorMap* tm_x, CUtensorMap* tm_w, const float* x, const float* weight, int B,
+                     int H, int W) {
     {
         // channels-last activations (B, H, W, 64): box = 32 channels x 128 frames of one row of one example
         const cuuint64_t dims[4] = {(cuuint64_t)kC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)kC * 4, (cuuint64_t)W * kC * 4, (cuuint64_t)H * W * kC * 4};
         const cuuint32_t box[4] = {32, (cuuint32_t)kTileW, 1, 1};
         const cuuint32_t es[4] = {1, 1, 1, 1};
-        const CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
+        const CUresult r = enc(tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(MODFX_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
@@ -584,14 +591,33 @@ int cnn_conv_tf32(const float* x, float* y, int B, int H, int W, int dil, const 
         const cuuint64_t strides[2] = {(cuuint64_t)kC * 4, (cuuint64_t)kC * kC * 4};
         const cuuint32_t box[3] = {32, (cuuint32_t)kC, 1};
         const cuuint32_t es[3] = {1, 1, 1};
-        const CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(weight), dims, strides, box, es,
+        const CUresult r = enc(tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(weight), dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(MODFX_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
     }
+    return MODFX_OK;
+}
+
+// x_lo / w_lo == nullptr: plain TF32 (one pass); otherwise the error-compensated three-pass form
+int cnn_conv_tf32(const float* x, const float* x_lo, float* y, int B, int H, int W, int dil, const float* weight,
+                  const float* w_lo, const float* bias, const float* prelu, cudaStream_t stream) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(MODFX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    MODFX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(w_lo) & 15) == 0,
+                  "x, y and weight must be 16-byte aligned");
+    MODFX_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "x_lo and w_lo go together");
+    ConvMaps tm;
+    int st = make_maps(enc, &tm.x[0], &tm.w[0], x, weight, B, H, W);
+    if (st != MODFX_OK) return st;
+    const bool split = x_lo != nullptr;
+    st = make_maps(enc, &tm.x[1], &tm.w[1], split ? x_lo : x, split ? w_lo : weight, B, H, W);
+    if (st != MODFX_OK) return st;
     MODFX_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     conv_tf32_kernel<<<dim3((W + kTileW - 1) / kTileW, (H + kRows - 1) / kRows, B), kThreads, kSmemBytes, stream>>>(
-        tm_x, tm_w, y, H, W, dil, bias, prelu);
+        tm, split ? 3 : 1, y, H, W, dil, bias, prelu);
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
 }

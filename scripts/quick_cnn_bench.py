@@ -60,7 +60,7 @@ ws = torch.empty(L.modfx_cnn_layernorm_workspace_bytes(B, 64, 128, W), dtype=tor
 ms = timed(lambda: _lib.check(L.modfx_cnn_layernorm_f32(_vp(y), _vp(y), B, 64, 128, W, 0, 1e-5, 1, _vp(ws), _stream())))
 print(f"layer norm of (B, 128, 345, 64): {ms:.3f} ms  {2 * y.numel() * 4 / ms / 1e6:.0f} GB/s (read twice + write once: x1.5)")
 
-for prec in precisions:
+for prec in precisions + (["tf32x3"] if "tf32" in precisions else []):
     net = Spectral2DCNN(in_ch=2, out_channels=[64] * 6, temp_dilations=DIL, pool_size=(2, 1), precision=prec).to(dev).eval()
     audio = torch.rand(B, 2, 88200, device=dev) - 0.5
     ms = timed(lambda: net(audio), n=3)
