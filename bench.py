@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extractor", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU-local CPUs")
     ap.add_argument("--gather-rendered", action="store_true",
                     help="N > 1: also time the optional all-gather of the rendered wet batch (outside the timed region)")
     ap.add_argument("--extractor-batch", type=int, default=128, help="clips per forward of the extractor side measurement")
@@ -225,6 +226,8 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    from mod_extraction_b200.sharding import bind_to_gpu_numa_node
+    numa_cpus = None if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)    # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -471,6 +474,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline, "extractor": extractor, "lfo_generation_s": lfo_gen_s, "metrics_gather_ms": gather_ms,
             "rendered_gather": rendered_gather,
+            "host_binding": None if numa_cpus is None else f"rank 0 pinned to {len(numa_cpus)} GPU-local CPUs (NVML affinity)",
             "wet_abs_mean": checksum,
         }
         print(json.dumps(line), flush=True)

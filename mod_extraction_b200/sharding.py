@@ -3,7 +3,8 @@ while rendering (examples are independent: every delay line is zeroed per call, 
 all-gather at the end for the rendered batch and/or per-rank metrics."""
 from __future__ import annotations
 
-from typing import List, Tuple
+import os
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -46,3 +47,25 @@ def max_over_ranks(value: float, device, group=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def bind_to_gpu_numa_node(gpu_index: int) -> Optional[List[int]]:
+    """One process per GPU: pin this process to the CPUs NVML reports as local to `gpu_index` BEFORE any pinned host
+    buffer is allocated, so that the staging buffers of the host-buffer path land on the GPU's own NUMA node instead
+    of wherever the launcher happened to start the process.  Returns the CPU list, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        cpus = [c for c in cpus if c < n_cpu]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
