@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -27,7 +27,7 @@ from torch import Tensor, nn
 
 from . import _lib
 
-__all__ = ["MelSpectrogram", "LogMelSpectrogram", "Spectral2DCNN", "mel_filterbank", "banded"]
+__all__ = ["MelSpectrogram", "LogMelSpectrogram", "Spectral2DCNN", "RandomLFO", "mel_filterbank", "banded"]
 
 
 def _hz_to_mel(f: float) -> float:
@@ -337,3 +337,34 @@ class Spectral2DCNN(nn.Module):
                     _vp(logmel), logmel.size(0) * logmel.size(1), logmel.size(-2), logmel.size(-1), f0, f1, t0, t1,
                     float(self.eps), 1, _stream()))
         return self.forward_features(logmel)
+
+
+class RandomLFO(nn.Module):
+    """Drop-in for ``mod_extraction.models.RandomLFO`` (models.py:19-69, configs/models/baseline_rand_lfo.yml): the
+    random-LFO baseline "model".  Same constructor and ``forward(batch_size, fx_params) -> (B, 1, n_samples)``; the
+    draws come from the torch global CPU generator in the reference's order (phase, frequency, shape per example),
+    the batch of LFOs is one launch (``modulations.make_rand_mod_signal``)."""
+
+    def __init__(self, n_samples: int, sr: float, use_shape_gt: bool = False, use_phase_gt: bool = False,
+                 use_freq_gt: bool = False, shapes: Optional[List[str]] = None, freq_min: float = 0.5,
+                 freq_max: float = 3.0, phase_error: float = 0.0, freq_error: float = 0.0) -> None:
+        super().__init__()
+        self.n_samples, self.sr = n_samples, sr
+        self.use_shape_gt, self.use_phase_gt, self.use_freq_gt = use_shape_gt, use_phase_gt, use_freq_gt
+        self.shapes, self.freq_min, self.freq_max = shapes, freq_min, freq_max
+        self.phase_error, self.freq_error = phase_error, freq_error
+
+    def forward(self, batch_size: int, fx_params: Optional[Dict[str, Tensor]] = None) -> Tensor:
+        from .modulations import make_rand_mod_signal
+        shapes_gt = phase_gt = freq_gt = None
+        if self.use_shape_gt:
+            assert fx_params is not None and "shape" in fx_params          # models.py:49
+            shapes_gt = fx_params["shape"]
+        if self.use_phase_gt:
+            assert fx_params is not None and "phase" in fx_params          # models.py:52
+            phase_gt = fx_params["phase"]
+        if self.use_freq_gt:
+            assert fx_params is not None and "rate_hz" in fx_params        # models.py:55
+            freq_gt = fx_params["rate_hz"]
+        return make_rand_mod_signal(batch_size, self.n_samples, self.sr, self.freq_min, self.freq_max, shapes_gt,
+                                    self.shapes, phase_gt, self.phase_error, freq_gt, self.freq_error).unsqueeze(1)

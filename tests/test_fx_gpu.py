@@ -283,6 +283,24 @@ def test_make_rand_mod_signal_same_draws_as_reference_order():
         assert np.abs(out[b] - ref).max() <= 1e-6
 
 
+def test_random_lfo_baseline_model_wrapper():
+    """models.RandomLFO (models.py:19-69, baseline_rand_lfo.yml: 345 frames at 172.5 Hz): same draws as a direct call."""
+    from mod_extraction_b200.models import RandomLFO
+    from mod_extraction_b200.modulations import make_rand_mod_signal
+    m = RandomLFO(n_samples=345, sr=172.5)
+    torch.manual_seed(7)
+    a = m(6)
+    torch.manual_seed(7)
+    b = make_rand_mod_signal(6, 345, 172.5, 0.5, 3.0, None, None, None, 0.0, None, 0.0)
+    assert a.shape == (6, 1, 345) and torch.equal(a.squeeze(1), b)
+    g = RandomLFO(n_samples=345, sr=172.5, use_freq_gt=True, use_phase_gt=True, use_shape_gt=True)
+    with pytest.raises(AssertionError):
+        g(2)                                                      # models.py:49: ground truth requested, none given
+    out = g(2, {"shape": ["tri", "cos"], "phase": torch.tensor([0.0, 1.0]), "rate_hz": torch.tensor([2.0, 1.0])})
+    ref = oracle.make_mod_signal(345, 172.5, 2.0, 0.0, "tri")
+    assert np.abs(out[0, 0].cpu().numpy() - ref).max() <= 1e-6
+
+
 def test_interp_bit_exact_vs_reference_goldens():
     from mod_extraction_b200.util import linear_interpolate_last_dim
     g = golden("interp")
