@@ -300,7 +300,7 @@ def main():
         "flanger": (lambda: _ops.flanger_chorus(dry, ModSource.control_rate(mod_lo), Rs.fl[0], Rs.fl[1], *fc_args,
                                                 example_index=i_fl, out=wet), i_fl.numel() * N * 8, 1),
         "chorus": (lambda: _ops.flanger_chorus(dry, ModSource.control_rate(mod_lo), Rs.ch[0], Rs.ch[1], *fc_args,
-                                               example_index=i_ch, out=wet), i_ch.numel() * N * 8, 1),
+                                               example_index=i_ch, out=wet), i_ch.numel() * N * 8, 2),
         "phaser": (lambda: _ops.phaser(dry2, float(SR), *ph_args, example_index=i_ph, out=wet2),
                    i_ph.numel() * N * 8, 4),
         "logmel": (lambda: Rs.front.forward_rows(dry2, N, B, logmel.view(-1), N, 2 * nm, None),
@@ -339,7 +339,7 @@ def main():
     dom = max(kernels, key=lambda k: kernels[k]["ms"] * (2 if k == "logmel" else 1))
     roofline = {"bound": "hbm", "kernel": {"logmel": "logmel_kernel (one launch over B dry rows; the wet half is a second identical launch)",
                                            "flanger": "fc_kernel<control-rate> (flanger group)",
-                                           "chorus": "fc_kernel<control-rate> (chorus group)",
+                                           "chorus": "fc_wide_kernel (chorus group)",
                                            "phaser": "phaser_{ctl,map,scan,run}_kernel (4 launches)"}[dom],
                 "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["gbs"] / peak,
                 "traffic": kernels[dom].get("dram_traffic_bytes"), "peak_source": peak_src,
@@ -470,7 +470,8 @@ def main():
                        "host RNG before the timed region; x100 upsample fused in the effect kernel",
                        "l2": "inputs (1.4 GB dry + 1.4 GB wet + 2.9 GB log-mel per step) far exceed the 126 MB L2",
                        "parallelism": f"batch-sharded x{world}, no collective while rendering"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * 10,      # per step: flanger 1 + chorus 1 + phaser 4 + log-mel 4
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * 11,      # per step: flanger 1 + chorus 2 (CTA-per-example kernel, then
+            # the one-warp kernel that only finds nothing left to do) + phaser 4 + log-mel 4
             "roofline": roofline,
             "cpu_baseline": cpu_baseline, "extractor": extractor, "lfo_generation_s": lfo_gen_s, "metrics_gather_ms": gather_ms,
             "rendered_gather": rendered_gather,

@@ -48,6 +48,7 @@ struct FcArgs {
     const float* mix_p;   float mix_s; float omm_s;   // scalar: f32(1.0 - mix) computed in double
     const int32_t* index;
     int n_items;
+    int wide;                       // 1: examples that qualify for fc_wide_kernel are rendered there and skipped here
 };
 
 enum ModMode { kAudioRate = 0, kControlRate = 1, kDirectLfo = 2 };
@@ -149,6 +150,131 @@ __device__ __noinline__ void serial_block(float* __restrict__ ring, int mask, in
     }
 }
 
+// ---- wide path: delay lines whose every tap lies more than a tile back (chorus) ------------------------------
+// With a minimum delay of D0 = min_delay_width * Mmin samples (485 for the reference's chorus) a sample never depends on
+// the previous kWideTile samples, so a whole CTA can render 384 samples of ONE delay line at a time -- four times the
+// warps per example of the one-warp kernel, which at 1365 examples leaves an SM with 9 warps.  Same per-sample
+// arithmetic (the branch-free form of fx.py:95-118 used by the one-warp kernel's fast path), so the bits are identical.
+// Whether an example qualifies is decided from its parameters and the extremes of its control-rate row by
+// wide_pred(), evaluated identically by both kernels: the wide kernel renders the example iff it holds, the one-warp
+// kernel iff it does not.
+constexpr int kWideThreads = 128;
+constexpr int kWideSub = 3;
+constexpr int kWideTile = kWideThreads * kWideSub;      // 384
+constexpr int kWideMargin = 4;                          // samples of slack on the delay bound (tap = ceil(delay) +- 1)
+
+__device__ __forceinline__ bool wide_pred(const Coef& c, float m_min, float m_max) {
+    const bool coef_ok = (c.A >= 0.0f) && (c.D0 >= 0.0f) && (__fadd_rn(c.A, c.D0) <= c.Mf);
+    const float d_min = __fadd_rn(__fmul_rn(c.A, m_min), c.D0);         // the delay is monotone in the modulation
+    return coef_ok && (m_min >= 0.0f) && (m_max <= 1.0f) && (d_min >= (float)(kWideTile + kWideMargin));
+}
+
+__device__ __forceinline__ void warp_minmax(float& mn, float& mx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    }
+}
+
+__device__ __forceinline__ Coef make_coef(const FcArgs& a, int b) {
+    Coef c;
+    c.M = a.M;
+    c.Mf = (float)a.M;
+    c.mask = a.ring_mask;
+    c.A = a.width_p ? __fmul_rn((float)a.Mlfo, a.width_p[b]) : a.lfo_delay_s;      // fx.py:98
+    c.D0 = a.mdw_p ? __fmul_rn(a.mdw_p[b], (float)a.Mmin) : a.min_delay_s;          // fx.py:97
+    c.fb = a.fb_p ? a.fb_p[b] : a.fb_s;
+    c.depth = a.depth_p ? a.depth_p[b] : a.depth_s;
+    c.mix = a.mix_p ? a.mix_p[b] : a.mix_s;
+    c.omm = a.mix_p ? __fsub_rn(1.0f, c.mix) : a.omm_s;                             // fx.py:117
+    return c;
+}
+
+__global__ void __launch_bounds__(kWideThreads) fc_wide_kernel(const FcArgs a, int wide_mask) {
+    extern __shared__ __align__(16) float ring[];           // written samples, indexed by time & wide_mask
+    __shared__ float red[2][kWideThreads / kWarp];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int item = blockIdx.x / a.C;
+    const int ch = blockIdx.x - item * a.C;
+    const int b = a.index ? a.index[item] : item;
+    const int N = a.N;
+    Coef c = make_coef(a, b);
+    const float* lo = a.mod + (int64_t)b * a.n_lo;
+
+    // extremes of the control-rate row -> does this example belong to the wide path?
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = tid; i < a.n_lo; i += kWideThreads) {
+        const float v = __ldg(lo + i);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+        if (!(v == v)) mx = INFINITY;                       // NaN: never eligible
+    }
+    warp_minmax(mn, mx);
+    if (lane == 0) { red[0][warp] = mn; red[1][warp] = mx; }
+    __syncthreads();
+    mn = red[0][0]; mx = red[1][0];
+#pragma unroll
+    for (int w = 1; w < kWideThreads / kWarp; ++w) { mn = fminf(mn, red[0][w]); mx = fmaxf(mx, red[1][w]); }
+    if (!wide_pred(c, mn, mx)) return;                      // left to the one-warp kernel (CTA-uniform)
+
+    const float* xs = a.x + ((int64_t)b * a.C + ch) * (int64_t)N;
+    float* ys = a.y + ((int64_t)b * a.C + ch) * (int64_t)N;
+    for (int i = tid; i <= wide_mask; i += kWideThreads) ring[i] = 0.0f;            // fx.py:92
+    int wk[kWideSub];
+    float xv[kWideSub];
+#pragma unroll
+    for (int k = 0; k < kWideSub; ++k) {
+        const int n = k * kWideThreads + tid;
+        wk[k] = n % c.M;
+        xv[k] = (n < N) ? __ldg(xs + n) : 0.0f;
+    }
+    const int last_lo = a.n_lo - 1;
+    __syncthreads();
+    for (int n0 = 0; n0 < N; n0 += kWideTile) {
+        float v[kWideSub], out[kWideSub];
+#pragma unroll
+        for (int k = 0; k < kWideSub; ++k) {
+            const int n = n0 + k * kWideThreads + tid;
+            // x100 upsample (util.py:15-29) and index arithmetic (fx.py:95-102), branch-free: 0 <= mod <= 1 and the
+            // parameter bounds keep (w - d) + M inside [0, 2M)
+            const float src = __fmul_rn(a.up_scale, (float)min(n, N - 1));
+            const int i0 = min((int)src, last_lo);
+            const float l1 = __fsub_rn(src, (float)i0);
+            const float l0 = __fsub_rn(1.0f, l1);
+            const float m = __fmaf_rn(l0, __ldg(lo + i0), __fmul_rn(l1, __ldg(lo + min(i0 + 1, last_lo))));
+            const float d = __fadd_rn(__fmul_rn(c.A, m), c.D0);                     // fx.py:98
+            const float t = __fadd_rn(__fsub_rn((float)wk[k], d), c.Mf);            // fx.py:99
+            const float r = (t >= c.Mf) ? __fsub_rn(t, c.Mf) : t;                   // % M
+            const float pf = floorf(r);
+            Samp sm;
+            sm.x = xv[k];
+            sm.fr = __fsub_rn(r, pf);                                                // fx.py:100
+            sm.omfr = __fsub_rn(1.0f, sm.fr);
+            int kp = wk[k] - (int)pf;                                                // fx.py:101
+            if (kp <= 0) kp += c.M;
+            sm.kp = kp;
+            const float vp = ring[(n - kp) & wide_mask];
+            const float vq = ring[(n - kq_of(kp, c.M)) & wide_mask];
+            fc_sample(sm, vp, vq, c, v[k], out[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kWideSub; ++k) {
+            const int n = n0 + k * kWideThreads + tid;
+            if (n < N) {
+                ring[n & wide_mask] = v[k];
+                ys[n] = out[k];
+            }
+            const int nn = n + kWideTile;                   // next tile's dry sample
+            xv[k] = (nn < N) ? __ldg(xs + nn) : 0.0f;
+            wk[k] += kWideTile;
+            if (wk[k] >= c.M) wk[k] -= c.M;
+            if (wk[k] >= c.M) wk[k] %= c.M;
+        }
+        __syncthreads();        // this tile's samples are in the ring before the next tile reads its taps
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -166,16 +292,20 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
     float* lo = mst;
     float* ring = mst + ((MODE == kAudioRate) ? kStages * kTile : ((MODE == kControlRate) ? (kLoWin + 4) : 0));
 
-    Coef c;
-    c.M = a.M;
-    c.Mf = (float)a.M;
-    c.mask = a.ring_mask;
-    c.A = a.width_p ? __fmul_rn((float)a.Mlfo, a.width_p[b]) : a.lfo_delay_s;      // fx.py:98
-    c.D0 = a.mdw_p ? __fmul_rn(a.mdw_p[b], (float)a.Mmin) : a.min_delay_s;          // fx.py:97
-    c.fb = a.fb_p ? a.fb_p[b] : a.fb_s;
-    c.depth = a.depth_p ? a.depth_p[b] : a.depth_s;
-    c.mix = a.mix_p ? a.mix_p[b] : a.mix_s;
-    c.omm = a.mix_p ? __fsub_rn(1.0f, c.mix) : a.omm_s;                             // fx.py:117
+    Coef c = make_coef(a, b);
+    if (MODE == kControlRate && a.wide) {
+        // examples whose every tap lies more than a wide tile back were rendered by fc_wide_kernel (same predicate)
+        const float* row = a.mod + (int64_t)b * a.n_lo;
+        float mn = INFINITY, mx = -INFINITY;
+        for (int i = lane; i < a.n_lo; i += kWarp) {
+            const float v = __ldg(row + i);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+            if (!(v == v)) mx = INFINITY;
+        }
+        warp_minmax(mn, mx);
+        if (wide_pred(c, mn, mx)) return;
+    }
     // With 0 <= mod <= 1 and these bounds the delay stays in [0, M], so (w - d) + M lies in [0, 2M) and
     // the reference's remainder is a single conditional subtraction (exact by Sterbenz).
     const bool coef_ok = (c.A >= 0.0f) && (c.D0 >= 0.0f) && (__fadd_rn(c.A, c.D0) <= c.Mf) && (a.M >= kTile);
@@ -571,6 +701,20 @@ extern "C" int modfx_flanger_chorus_f32(const float* x, float* y, int32_t B, int
                     a.M, a.n_lo, smem);
     const dim3 grid((unsigned)((int64_t)a.n_items * C));
     cudaStream_t s = as_stream(stream);
+    // Delay lines that can never reach back less than a wide tile (min_delay_width * Mmin >= 388 samples: the chorus) go
+    // through the CTA-per-example kernel first; the one-warp kernel then skips exactly those examples.
+    a.wide = 0;
+    if (mode == kControlRate && !a.lfo_freq && Mmin >= kWideTile + kWideMargin) {
+        const int wring = next_pow2(a.M + kWideTile);
+        const size_t wsmem = sizeof(float) * (size_t)wring;
+        if (wsmem <= 200 * 1024) {
+            if (wsmem > 48 * 1024)
+                MODFX_CUDA_OK(cudaFuncSetAttribute(fc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            a.wide = 1;
+            fc_wide_kernel<<<grid, kWideThreads, wsmem, s>>>(a, wring - 1);
+            MODFX_CUDA_OK(cudaGetLastError());
+        }
+    }
 #define LAUNCH_FC(MODE)                                                                                   \
     do {                                                                                                  \
         if (smem > 48 * 1024)                                                                             \
