@@ -395,30 +395,31 @@ def main():
     extractor = None
     if not args.no_extractor:
         from mod_extraction_b200.models import Spectral2DCNN
-        net = Spectral2DCNN(in_ch=2, n_samples=N, sr=SR, out_channels=[64] * 6, temp_dilations=[1, 1, 2, 4, 8, 16],
-                            pool_size=(2, 1), precision="tf32").to(dev).eval()
         Bx = min(args.extractor_batch, B)
         feats = logmel[:Bx]
-        for _ in range(2):
-            net.forward_features(feats)
-        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        x0.record()
-        for _ in range(reps):
-            out_x, _ = net.forward_features(feats)
-        x1.record()
-        torch.cuda.synchronize()
-        ms_x = x0.elapsed_time(x1) / reps
         flops = 2.0 * 65 * 64 * 345 * (256 * 2 + 64 * (128 + 64 + 32 + 16 + 8)) * Bx      # the six convolutions
-        tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
         extractor = {"what": "Spectral2DCNN body on the log-mel of this step (6 x {layer norm, 5x13 conv + pool + PReLU on "
-                             "tcgen05 TF32}, head), random weights", "batch": Bx, "ms": ms_x,
-                     "audio_s_per_s": Bx * (N / SR) / (ms_x * 1e-3), "conv_tflops": flops / (ms_x * 1e-3) / 1e12,
-                     "tf32_peak_tflops": tf32_peak,
-                     "tf32_peak_source": "half of MEASURED_PEAKS.json bf16_tflops (no TF32 figure is measured by the driver)",
-                     "frac_of_tf32_peak": flops / (ms_x * 1e-3) / 1e12 / tf32_peak, "gpu_launches_per_forward": 19,
-                     "output_mean": float(out_x.mean().item())}
-        del net
+                             "tcgen05}, head), random weights", "batch": Bx, "gpu_launches_per_forward": 19,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops for float16 operands, half of it for TF32 (the driver "
+                                    "measures no TF32 figure)"}
+        for prec, peak in (("tf32", bf16_peak / 2.0), ("fp16", bf16_peak)):
+            net = Spectral2DCNN(in_ch=2, n_samples=N, sr=SR, out_channels=[64] * 6, temp_dilations=[1, 1, 2, 4, 8, 16],
+                                pool_size=(2, 1), precision=prec).to(dev).eval()
+            for _ in range(2):
+                net.forward_features(feats)
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            x0.record()
+            for _ in range(reps):
+                out_x, _ = net.forward_features(feats)
+            x1.record()
+            torch.cuda.synchronize()
+            ms_x = x0.elapsed_time(x1) / reps
+            extractor[prec] = {"ms": ms_x, "audio_s_per_s": Bx * (N / SR) / (ms_x * 1e-3),
+                               "conv_tflops": flops / (ms_x * 1e-3) / 1e12, "peak_tflops": peak,
+                               "frac_of_peak": flops / (ms_x * 1e-3) / 1e12 / peak, "output_mean": float(out_x.mean().item())}
+            del net
 
     # ---------------- final gather of per-rank metrics (the only collective, outside the timed region)
     checksum = float(wet.double().abs().mean().item())

@@ -221,7 +221,9 @@ int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, c
  *                             alias x when both are channels-last.  round_tf32 = 1 rounds y to TF32
  *                             (round-to-nearest), the operand format of the tensor-core convolution;
  *                             round_tf32 = 2 writes the error-compensated split instead: y holds TWO planes of
- *                             B*H*W*C floats, hi = tf32(v) and lo = tf32(v - hi) (channels-last input, y != x).
+ *                             B*H*W*C floats, hi = tf32(v) and lo = tf32(v - hi) (channels-last input, y != x);
+ *                             round_tf32 = 3 writes y as (B, H, W, C) IEEE float16 (round-to-nearest), the
+ *                             operand format of modfx_cnn_conv_pool_prelu_f16_f32.
  *                             workspace: modfx_cnn_layernorm_workspace_bytes(B, C, H, W) bytes.
  *   modfx_cnn_conv_pool_prelu_f32
  *                             replaces Conv2d(Cin, Cout, (KH, KW), dilation=(1, dil_w), padding="same")
@@ -242,6 +244,12 @@ int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, c
  *                             rounding error is gone (the dropped lo*lo term is ~2^-22 relative); what remains is
  *                             the tensor pipe's truncating accumulator: 2e-4 per layer where plain TF32 has
  *                             1e-3, and float32-grade results through the whole network.
+ *   modfx_cnn_conv_pool_prelu_f16_f32
+ *                             the same layer (Cin = Cout = 64) with float16 operands (x (B, H, W, 64) and weight
+ *                             (5, 13, 64, 64) as IEEE half) and float32 accumulation / output on the tensor cores.
+ *                             float16 has TF32's 11 significant bits and normalised activations / weights sit
+ *                             inside its range, so the parity bars are those of MODFX_CNN_TF32 -- at twice the
+ *                             MMA rate and half the operand traffic.
  *   modfx_cnn_head_f32        replaces tr.mean(x, dim=-2), Conv1d(C, L, 1) and tr.sigmoid,
  *                             models.py:210-214: x (B, H, W, C) -> latent (B, C, W), out (B, L, W).
  *                             weight (L, C), bias (L,).
@@ -261,6 +269,8 @@ int modfx_cnn_conv_pool_prelu_f32(const float* x, float* y, int32_t B, int32_t H
 int modfx_cnn_conv_pool_prelu_tf32x3_f32(const float* x_hi, const float* x_lo, float* y, int32_t B, int32_t H,
                                          int32_t W, int32_t dil_w, const float* w_hi, const float* w_lo,
                                          const float* bias, const float* prelu, void* stream);
+int modfx_cnn_conv_pool_prelu_f16_f32(const void* x_f16, float* y, int32_t B, int32_t H, int32_t W, int32_t dil_w,
+                                      const void* w_f16, const float* bias, const float* prelu, void* stream);
 int modfx_cnn_head_f32(const float* x, float* latent, float* out, int32_t B, int32_t H, int32_t W, int32_t C,
                        int32_t L, const float* weight, const float* bias, void* stream);
 

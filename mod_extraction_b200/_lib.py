@@ -39,6 +39,7 @@ class ModfxModSource(ctypes.Structure):
 
 MOD_AUDIO_RATE, MOD_CONTROL_RATE, MOD_LFO = 0, 1, 2
 CNN_FP32, CNN_TF32 = 0, 1      # modfx_cnn_precision
+CNN_FP16 = 3                   # python-side tag only: modfx_cnn_conv_pool_prelu_f16_f32
 CNN_TF32X3 = 2                 # python-side tag only: the split entry point modfx_cnn_conv_pool_prelu_tf32x3_f32
 
 SHAPES = ["cos", "rect_cos", "inv_rect_cos", "tri", "saw", "rsaw", "sqr"]   # modfx_shape order
@@ -76,6 +77,7 @@ _SIGNATURES = {
     "modfx_cnn_conv_pool_prelu_f32": ([_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp],
                                       ctypes.c_int),
     "modfx_cnn_conv_pool_prelu_tf32x3_f32": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "modfx_cnn_conv_pool_prelu_f16_f32": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp], ctypes.c_int),
     "modfx_cnn_head_f32": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], ctypes.c_int),
     "modfx_phaser_workspace_bytes": ([_i32, _i64], _i64),
     "modfx_phaser_f32": ([_vp, _vp, _i32, _i64, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp],

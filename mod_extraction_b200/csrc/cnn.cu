@@ -10,12 +10,14 @@
 // layer, 3 % of the network's flops); layers 2..6 normally run on tcgen05 (MODFX_CNN_TF32).
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 namespace modfx {
 
-int cnn_conv_tf32(const float* x, const float* x_lo, float* y, int B, int H, int W, int dil_w, const float* weight,
-                  const float* w_lo, const float* bias, const float* prelu, cudaStream_t stream);      // cnn_tc.cu
+int cnn_conv_tf32(const void* x, const void* x_lo, float* y, int B, int H, int W, int dil_w, const void* weight,
+                  const void* w_lo, const float* bias, const float* prelu, bool half, cudaStream_t stream);   // cnn_tc.cu
 int cnn_conv1_tf32(const float* x, float* y, int B, int H, int W, const float* weight, const float* bias,
                    const float* prelu, cudaStream_t stream);     // cnn_tc.cu (2 input channels, dilation 1)
 
@@ -107,6 +109,12 @@ __global__ void __launch_bounds__(kLnThreads) ln_apply_kernel(const float* __res
             v.y = (v.y - s_stat[c + 1]) * s_stat[C + c + 1];
             v.z = (v.z - s_stat[c + 2]) * s_stat[C + c + 2];
             v.w = (v.w - s_stat[c + 3]) * s_stat[C + c + 3];
+            if (round == 3) {       // float16 operands of the tensor-core convolution (round-to-nearest)
+                __half2* yh = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(y) + b * n + e);
+                yh[0] = __floats2half2_rn(v.x, v.y);
+                yh[1] = __floats2half2_rn(v.z, v.w);
+                continue;
+            }
             if (round == 2) {       // error-compensated TF32: hi plane here, lo = tf32(v - hi) one plane further
                 const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
                 *reinterpret_cast<float4*>(yb + e) = h;
@@ -287,9 +295,9 @@ extern "C" int modfx_cnn_layernorm_f32(const float* x, float* y, int32_t B, int3
     MODFX_REQUIRE(x && y && workspace, "NULL pointer");
     MODFX_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
     MODFX_REQUIRE(!(x_is_nchw && x == y), "in-place needs a channels-last input");
-    MODFX_REQUIRE(round_tf32 >= 0 && round_tf32 <= 2, "round_tf32=%d", round_tf32);
-    if (round_tf32 == 2 && (x_is_nchw || (C & 3) || x == y))
-        return fail(MODFX_ERR_UNSUPPORTED, "the hi/lo split needs a channels-last input, C %% 4 == 0 and y != x");
+    MODFX_REQUIRE(round_tf32 >= 0 && round_tf32 <= 3, "round_tf32=%d", round_tf32);
+    if (round_tf32 >= 2 && (x_is_nchw || (C & 3) || x == y))
+        return fail(MODFX_ERR_UNSUPPORTED, "the hi/lo split and the float16 output need a channels-last input, C %% 4 == 0 and y != x");
     if (kLnThreads % C != 0 && !x_is_nchw)
         return fail(MODFX_ERR_UNSUPPORTED, "C=%d: the channel count must divide %d", C, kLnThreads);
     if (C > 1024) return fail(MODFX_ERR_UNSUPPORTED, "C=%d too large", C);
@@ -347,7 +355,7 @@ extern "C" int modfx_cnn_conv_pool_prelu_f32(const float* x, float* y, int32_t B
         if (Cin != 64)
             return fail(MODFX_ERR_UNSUPPORTED, "the tensor-core convolution is built for Cin=64, and Cin=2 with dilation 1 (got %d, %d)",
                         Cin, dil_w);
-        return cnn_conv_tf32(x, nullptr, y, B, H, W, dil_w, weight, nullptr, bias, prelu, st);
+        return cnn_conv_tf32(x, nullptr, y, B, H, W, dil_w, weight, nullptr, bias, prelu, false, st);
     }
     if (precision != MODFX_CNN_FP32) return fail(MODFX_ERR_INVALID, "precision=%d", precision);
     if (Cin == 2) return launch_conv_fp32<2, 2>(x, y, B, H, W, dil_w, weight, bias, prelu, st);
@@ -365,7 +373,20 @@ extern "C" int modfx_cnn_conv_pool_prelu_tf32x3_f32(const float* x_hi, const flo
         return fail(MODFX_ERR_UNSUPPORTED, "H=%d must be even and the time dilation %d in [1, %d]", H, dil_w, kMaxDil);
     if (B == 0) return MODFX_OK;
     MODFX_REQUIRE(B <= 65535 && H / 2 <= 65535, "grid too large");
-    return cnn_conv_tf32(x_hi, x_lo, y, B, H, W, dil_w, w_hi, w_lo, bias, prelu, as_stream(stream));
+    return cnn_conv_tf32(x_hi, x_lo, y, B, H, W, dil_w, w_hi, w_lo, bias, prelu, false, as_stream(stream));
+}
+
+extern "C" int modfx_cnn_conv_pool_prelu_f16_f32(const void* x_f16, float* y, int32_t B, int32_t H, int32_t W,
+                                                 int32_t dil_w, const void* w_f16, const float* bias, const float* prelu,
+                                                 void* stream) {
+    MODFX_REQUIRE(x_f16 && y && w_f16 && bias && prelu, "NULL pointer");
+    MODFX_REQUIRE(B >= 0 && H >= 2 && W >= 1, "bad shape B=%d H=%d W=%d", B, H, W);
+    MODFX_REQUIRE(x_f16 != (const void*)y, "x and y must not alias");
+    if ((H & 1) || dil_w < 1 || dil_w > kMaxDil)
+        return fail(MODFX_ERR_UNSUPPORTED, "H=%d must be even and the time dilation %d in [1, %d]", H, dil_w, kMaxDil);
+    if (B == 0) return MODFX_OK;
+    MODFX_REQUIRE(B <= 65535 && H / 2 <= 65535, "grid too large");
+    return cnn_conv_tf32(x_f16, nullptr, y, B, H, W, dil_w, w_f16, nullptr, bias, prelu, true, as_stream(stream));
 }
 
 extern "C" int modfx_cnn_head_f32(const float* x, float* latent, float* out, int32_t B, int32_t H, int32_t W,

@@ -32,22 +32,34 @@ constexpr int kKH = 5, kKW = 13;
 constexpr int kTileW = 128;               // frames per CTA = UMMA M
 constexpr int kRows = 8;                  // conv rows per CTA = accumulators in tensor memory (8 x 64 = 512 columns)
 constexpr int kInRows = kRows + kKH - 1;  // input rows a CTA walks
-constexpr int kAStages = 4;               // power of two
-constexpr int kPanelA = kTileW * 128;     // bytes: 128 frames x 32 channels (one 128-byte swizzle row per frame)
-constexpr int kStageA = 2 * kPanelA;      // 32 KB: both channel halves
-constexpr int kTileB = kC * 128;          // bytes: 64 output channels x 32 input channels of one kernel tap
+constexpr int kPanelA = kTileW * 128;     // bytes: 128 frames x one 128-byte swizzle row (32 float32 / 64 float16 channels)
+constexpr int kTileB = kC * 128;          // bytes: 64 output channels x one 128-byte row of input channels of a kernel tap
 constexpr int kPanelB = kKH * kTileB;     // 40 KB: the 5 kernel rows of one kw, kh = 4 first
-constexpr int kBytesB = 2 * kPanelB;      // 80 KB
+
+// Operand format of the 64 -> 64 convolution.  float32 storage read as TF32 (two 128-byte panels of 32 channels per tap,
+// K = 8 per MMA) or float16 storage (one panel of 64 channels, K = 16 per MMA): float16 has TF32's 11 significant bits,
+// and normalised activations / weights sit well inside its range, so the parity bars are the same -- at twice the MMA
+// rate and half the operand traffic.
+template <bool kHalf>
+struct Fmt {
+    static constexpr int kPanels = kHalf ? 1 : 2;
+    static constexpr int kChanPerPanel = kC / kPanels;
+    static constexpr int kStageA = kPanels * kPanelA;           // 32 KB / 16 KB
+    static constexpr int kBytesB = kPanels * kPanelB;           // 80 KB / 40 KB
+    static constexpr int kAStages = kHalf ? 8 : 4;              // power of two; 128 KB of A in flight either way
+    static constexpr int kNumBars = 2 * kAStages + 2 * kKH + 1;
+    static constexpr int kSmemBytes = kAStages * kStageA + kBytesB + 1024 /* alignment slack */ + 8 * kNumBars + 16;
+    static constexpr uint32_t kFormat = kHalf ? 0u : 2u;        // instruction descriptor: F16 = 0, TF32 = 2
+};
 constexpr int kThreads = 8 * 32;
 constexpr int kTmemCols = kRows * kC;     // 512: all of tensor memory
-constexpr int kNumBars = 2 * kAStages + 2 * kKH + 1;
-constexpr int kSmemBytes = kAStages * kStageA + kBytesB + 1024 /* alignment slack */ + 8 * kNumBars + 16;
 
 // kind::tf32 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28
-__device__ __forceinline__ uint32_t idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileW >> 4) << 24);
+__device__ __forceinline__ uint32_t idesc_fmt(int n, uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileW >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t idesc_tf32(int n) { return idesc_fmt(n, 2u); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,6 +118,14 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -155,10 +175,13 @@ struct ConvMaps {
     CUtensorMap w[2];       // weights: hi, lo
 };
 
+template <bool kHalf>
 __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_constant__ ConvMaps tm, int n_pass,
                                                                 float* __restrict__ y, int H, int W, int dil,
                                                                 const float* __restrict__ bias,
                                                                 const float* __restrict__ prelu) {
+    using F = Fmt<kHalf>;
+    constexpr int kAStages = F::kAStages, kStageA = F::kStageA, kBytesB = F::kBytesB, kNumBars = F::kNumBars;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B wants 1024-byte aligned tiles
@@ -220,8 +243,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
                     const uint32_t full = bar_afull + 8 * s;
                     const uint32_t st = a_base + s * kStageA;
                     mbar_expect_tx(full, kStageA);
-                    tma_load_4d(st, tmx, full, 0, wx, plan.h0 - kKH / 2 + r, b);
-                    tma_load_4d(st + kPanelA, tmx, full, 32, wx, plan.h0 - kKH / 2 + r, b);
+#pragma unroll
+                    for (int p = 0; p < F::kPanels; ++p)
+                        tma_load_4d(st + p * kPanelA, tmx, full, p * F::kChanPerPanel, wx, plan.h0 - kKH / 2 + r, b);
                 }
                 __syncwarp();
                 ++it;
@@ -238,9 +262,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
                 mbar_wait(bar_bempty + 8 * j, ((uint32_t)v & 1u) ^ 1u);
                 if (elect_one()) {
                     const uint32_t full = bar_bfull + 8 * j;
-                    mbar_expect_tx(full, 2 * kTileB);
-                    tma_load_3d(b_base + j * kTileB, tmw, full, 0, 0, kh * kKW + kw);
-                    tma_load_3d(b_base + kPanelB + j * kTileB, tmw, full, 32, 0, kh * kKW + kw);
+                    mbar_expect_tx(full, F::kPanels * kTileB);
+#pragma unroll
+                    for (int p = 0; p < F::kPanels; ++p)
+                        tma_load_3d(b_base + p * kPanelB + j * kTileB, tmw, full, p * F::kChanPerPanel, 0, kh * kKW + kw);
                 }
                 __syncwarp();
             }
@@ -289,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
                     if ((wait_b[r] >> kh) & 1u) mbar_wait(bar_bfull + 8 * (kKH - 1 - kh), b_par);
                 // (waited for even when this issuer has no accumulator under the row: it keeps the two issuers within
                 // one ring revolution of each other, which the two-arrival "empty" barriers rely on)
-                mbar_wait(bar_afull + 8 * s, ((uint32_t)it >> 2) & 1u);
+                mbar_wait(bar_afull + 8 * s, ((uint32_t)(it / kAStages)) & 1u);
                 if (run_n[r] > 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_lo = umma_desc_lo(a_base) + s * (kStageA >> 4);
@@ -301,14 +326,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
                         int n = 1;
                         while (n < left && ((started >> (a + n)) & 1u) == flag) ++n;
                         const uint32_t b_lo = umma_desc_lo(b_base) + (kKH - 1 - (r - a)) * (kTileB >> 4);
-                        const uint32_t idesc = idesc_tf32(n * kC);
+                        const uint32_t idesc = idesc_fmt(n * kC, F::kFormat);
                         const uint32_t d = tmem + a * kC;
                         if (elect_one()) {
 #pragma unroll
-                            for (int pk = 0; pk < 8; ++pk) {
+                            for (int pk = 0; pk < 4 * F::kPanels; ++pk) {        // 32 bytes of K per instruction
                                 const int p = pk >> 2, k = pk & 3;
-                                umma_tf32(d, umma_desc(a_lo + ((p * kPanelA + k * 32) >> 4)),
-                                          umma_desc(b_lo + ((p * kPanelB + k * 32) >> 4)), idesc, flag | (pk > 0));
+                                const uint64_t ad = umma_desc(a_lo + ((p * kPanelA + k * 32) >> 4));
+                                const uint64_t bd = umma_desc(b_lo + ((p * kPanelB + k * 32) >> 4));
+                                if (kHalf) umma_f16(d, ad, bd, idesc, flag | (pk > 0));
+                                else umma_tf32(d, ad, bd, idesc, flag | (pk > 0));
                             }
                         }
                         __syncwarp();
@@ -572,26 +599,29 @@ EncodeTiledFn encode_tiled() {
 
 }  // namespace
 
-static int make_maps(EncodeTiledFn enc, CUtensorMap* tm_x, CUtensorMap* tm_w, const float* x, const float* weight, int B,
-                     int H, int W) {
+static int make_maps(EncodeTiledFn enc, CUtensorMap* tm_x, CUtensorMap* tm_w, const void* x, const void* weight, int B,
+                     int H, int W, bool half) {
+    const cuuint64_t eb = half ? 2 : 4;                          // bytes per element
+    const cuuint32_t row = (cuuint32_t)(128 / eb);               // channels in one 128-byte swizzle row
+    const CUtensorMapDataType dt = half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     {
-        // channels-last activations (B, H, W, 64): box = 32 channels x 128 frames of one row of one example
+        // channels-last activations (B, H, W, 64): box = one 128-byte row of channels x 128 frames of one image row
         const cuuint64_t dims[4] = {(cuuint64_t)kC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        const cuuint64_t strides[3] = {(cuuint64_t)kC * 4, (cuuint64_t)W * kC * 4, (cuuint64_t)H * W * kC * 4};
-        const cuuint32_t box[4] = {32, (cuuint32_t)kTileW, 1, 1};
+        const cuuint64_t strides[3] = {(cuuint64_t)kC * eb, (cuuint64_t)W * kC * eb, (cuuint64_t)H * W * kC * eb};
+        const cuuint32_t box[4] = {row, (cuuint32_t)kTileW, 1, 1};
         const cuuint32_t es[4] = {1, 1, 1, 1};
-        const CUresult r = enc(tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
+        const CUresult r = enc(tm_x, dt, 4, const_cast<void*>(x), dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(MODFX_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
     }
     {
-        // weights (KH, KW, Cout, Cin) = (tap, out channel, in channel): box = 32 in x 64 out channels of one tap
+        // weights (KH, KW, Cout, Cin) = (tap, out channel, in channel): box = one row of in x 64 out channels of one tap
         const cuuint64_t dims[3] = {(cuuint64_t)kC, (cuuint64_t)kC, (cuuint64_t)(kKH * kKW)};
-        const cuuint64_t strides[2] = {(cuuint64_t)kC * 4, (cuuint64_t)kC * kC * 4};
-        const cuuint32_t box[3] = {32, (cuuint32_t)kC, 1};
+        const cuuint64_t strides[2] = {(cuuint64_t)kC * eb, (cuuint64_t)kC * kC * eb};
+        const cuuint32_t box[3] = {row, (cuuint32_t)kC, 1};
         const cuuint32_t es[3] = {1, 1, 1};
-        const CUresult r = enc(tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(weight), dims, strides, box, es,
+        const CUresult r = enc(tm_w, dt, 3, const_cast<void*>(weight), dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(MODFX_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
@@ -599,9 +629,10 @@ static int make_maps(EncodeTiledFn enc, CUtensorMap* tm_x, CUtensorMap* tm_w, co
     return MODFX_OK;
 }
 
-// x_lo / w_lo == nullptr: plain TF32 (one pass); otherwise the error-compensated three-pass form
-int cnn_conv_tf32(const float* x, const float* x_lo, float* y, int B, int H, int W, int dil, const float* weight,
-                  const float* w_lo, const float* bias, const float* prelu, cudaStream_t stream) {
+// x_lo / w_lo == nullptr: one pass (TF32 on float32 storage, or float16 storage when `half`); otherwise the
+// error-compensated three-pass TF32 form
+int cnn_conv_tf32(const void* x, const void* x_lo, float* y, int B, int H, int W, int dil, const void* weight,
+                  const void* w_lo, const float* bias, const float* prelu, bool half, cudaStream_t stream) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(MODFX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     MODFX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
@@ -609,15 +640,24 @@ int cnn_conv_tf32(const float* x, const float* x_lo, float* y, int B, int H, int
                       (reinterpret_cast<uintptr_t>(w_lo) & 15) == 0,
                   "x, y and weight must be 16-byte aligned");
     MODFX_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "x_lo and w_lo go together");
-    ConvMaps tm;
-    int st = make_maps(enc, &tm.x[0], &tm.w[0], x, weight, B, H, W);
-    if (st != MODFX_OK) return st;
     const bool split = x_lo != nullptr;
-    st = make_maps(enc, &tm.x[1], &tm.w[1], split ? x_lo : x, split ? w_lo : weight, B, H, W);
+    MODFX_REQUIRE(!(split && half), "the three-pass form is TF32 only");
+    ConvMaps tm;
+    int st = make_maps(enc, &tm.x[0], &tm.w[0], x, weight, B, H, W, half);
     if (st != MODFX_OK) return st;
-    MODFX_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    conv_tf32_kernel<<<dim3((W + kTileW - 1) / kTileW, (H + kRows - 1) / kRows, B), kThreads, kSmemBytes, stream>>>(
-        tm, split ? 3 : 1, y, H, W, dil, bias, prelu);
+    st = make_maps(enc, &tm.x[1], &tm.w[1], split ? x_lo : x, split ? w_lo : weight, B, H, W, half);
+    if (st != MODFX_OK) return st;
+    const dim3 grid((W + kTileW - 1) / kTileW, (H + kRows - 1) / kRows, B);
+    if (half) {
+        MODFX_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Fmt<true>::kSmemBytes));
+        conv_tf32_kernel<true><<<grid, kThreads, Fmt<true>::kSmemBytes, stream>>>(tm, 1, y, H, W, dil, bias, prelu);
+    } else {
+        MODFX_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Fmt<false>::kSmemBytes));
+        conv_tf32_kernel<false><<<grid, kThreads, Fmt<false>::kSmemBytes, stream>>>(tm, split ? 3 : 1, y, H, W, dil, bias,
+                                                                                   prelu);
+    }
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
 }

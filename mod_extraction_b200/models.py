@@ -188,7 +188,8 @@ class Spectral2DCNN(nn.Module):
     Same constructor arguments, same ``forward(x) -> (x, latent)`` with x (B, in_ch, n_samples) ->
     (B, latent_dim, n_frames) and latent (B, out_channels[-1], n_frames), and the same parameter names, so
     ``load_state_dict`` takes a reference checkpoint unchanged (the torch sub-modules below only hold the
-    parameters; the arithmetic runs in libmodfx).  ``precision``: "tf32" (tcgen05, default), "tf32x3" (tcgen05 with
+    parameters; the arithmetic runs in libmodfx).  ``precision``: "tf32" (tcgen05, default), "fp16" (tcgen05 with
+    float16 operand storage for the 64-channel layers: TF32's 11 significant bits at twice the rate), "tf32x3" (tcgen05 with
     error-compensated operands: meets the float32 parity bars of the network at a third of the TF32 rate, 6x faster than
     the CUDA-core path) or "fp32" (CUDA cores, exact float32 FMAs).
     Built: kernel_size (5, 13), pool_size (2, 1), 64 channels per layer, bin dilation 1, use_ln=True.
@@ -215,7 +216,7 @@ class Spectral2DCNN(nn.Module):
                 "modfx builds the shipped lfo_2dcnn (configs/models/spectral_2dcnn.yml): in_ch 2, kernel (5, 13), "
                 "pool (2, 1), 64 channels per layer, bin dilation 1, use_ln")
         assert n_mels % (2 ** len(out_channels)) == 0, "n_mels must survive the 2x1 pools"
-        assert precision in ("tf32", "tf32x3", "fp32")
+        assert precision in ("fp16", "tf32", "tf32x3", "fp32")
         self.in_ch, self.n_samples, self.sr, self.n_fft, self.hop_len, self.n_mels = in_ch, n_samples, sr, n_fft, hop_len, n_mels
         self.kernel_size, self.pool_size, self.latent_dim = tuple(kernel_size), tuple(pool_size), latent_dim
         self.freq_mask_amount, self.time_mask_amount, self.use_ln, self.eps = freq_mask_amount, time_mask_amount, use_ln, eps
@@ -264,9 +265,12 @@ class Spectral2DCNN(nn.Module):
                 conv, act = self.cnn[4 * i + 1], self.cnn[4 * i + 3]
                 w = conv.weight.detach().to(device=device, dtype=torch.float32).permute(2, 3, 0, 1).contiguous()
                 # tensor-core layers: 64 input channels, or the 2-channel first layer when it is not dilated
-                tc = self.precision == "tf32" and (w.size(3) == 64 or (w.size(3) == 2 and self.temp_dilations[i] == 1))
+                tc = self.precision in ("tf32", "fp16") and (w.size(3) == 64 or (w.size(3) == 2 and self.temp_dilations[i] == 1))
                 x3 = self.precision == "tf32x3" and w.size(3) == 64
                 mode = _lib.CNN_TF32 if tc else (_lib.CNN_TF32X3 if x3 else _lib.CNN_FP32)
+                if self.precision == "fp16" and w.size(3) == 64:
+                    mode, tc = _lib.CNN_FP16, False
+                    w = w.to(torch.float16)            # round-to-nearest: the 11 significant bits TF32 keeps
                 if tc:
                     w = round_to_tf32(w)
                 elif x3:                                   # w = hi + lo, both exactly representable in TF32
@@ -301,7 +305,10 @@ class Spectral2DCNN(nn.Module):
                                                  1 if packed[0][3] == _lib.CNN_TF32 else 0, _vp(ws), _stream()))
             for i, (w, bias, slope, prec) in enumerate(packed):
                 y = torch.empty((B, H // 2, W, 64), dtype=torch.float32, device=dev)
-                if prec == _lib.CNN_TF32X3:                # x holds the hi and lo planes, w likewise
+                if prec == _lib.CNN_FP16:                  # x and w are float16
+                    _lib.check(L.modfx_cnn_conv_pool_prelu_f16_f32(_vp(x), _vp(y), B, H, W, self.temp_dilations[i], _vp(w),
+                                                                  _vp(bias), _vp(slope), _stream()))
+                elif prec == _lib.CNN_TF32X3:              # x holds the hi and lo planes, w likewise
                     _lib.check(L.modfx_cnn_conv_pool_prelu_tf32x3_f32(_vp(x[0]), _vp(x[1]), _vp(y), B, H, W, self.temp_dilations[i],
                                                                      _vp(w[0]), _vp(w[1]), _vp(bias), _vp(slope), _stream()))
                 else:
@@ -310,7 +317,10 @@ class Spectral2DCNN(nn.Module):
                 H, C, x = H // 2, 64, y
                 if i + 1 < len(packed):
                     nxt = packed[i + 1][3]
-                    if nxt == _lib.CNN_TF32X3:             # normalise into the two-plane hi / lo split
+                    if nxt == _lib.CNN_FP16:               # normalise into float16
+                        x = torch.empty((B, H, W, C), dtype=torch.float16, device=dev)
+                        _lib.check(L.modfx_cnn_layernorm_f32(_vp(y), _vp(x), B, C, H, W, 0, self.ln_eps, 3, _vp(ws), _stream()))
+                    elif nxt == _lib.CNN_TF32X3:           # normalise into the two-plane hi / lo split
                         x = torch.empty((2, B, H, W, C), dtype=torch.float32, device=dev)
                         _lib.check(L.modfx_cnn_layernorm_f32(_vp(y), _vp(x), B, C, H, W, 0, self.ln_eps, 2, _vp(ws), _stream()))
                     else:

@@ -47,6 +47,20 @@ for prec in precisions:
         print(f"{prec} layer {i + 1}: H={H:3d} dil={DIL[i]:2d}  {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s")
     print(f"{prec} layers 2-6: {total:.3f} ms for B={B} ({total / B * 1e3:.1f} us per example)")
 
+if "tf32" in precisions:
+    total = 0.0
+    for i in range(1, 6):
+        H = 256 >> i
+        xh = torch.randn(B, H, W, 64, device=dev).half()
+        wh = (torch.randn(5, 13, 64, 64, device=dev) * 0.02).half()
+        b = torch.zeros(64, device=dev)
+        y = torch.empty(B, H // 2, W, 64, device=dev)
+        ms = timed(lambda: _lib.check(L.modfx_cnn_conv_pool_prelu_f16_f32(_vp(xh), _vp(y), B, H, W, DIL[i], _vp(wh), _vp(b), _vp(b),
+                                                                          _stream())))
+        total += ms
+        print(f"fp16 layer {i + 1}: H={H:3d} dil={DIL[i]:2d}  {ms:8.3f} ms  {2.0 * B * H * W * 64 * 64 * 65 / ms / 1e9:7.1f} TFLOP/s")
+    print(f"fp16 layers 2-6: {total:.3f} ms for B={B} ({total / B * 1e3:.1f} us per example)")
+
 x = torch.randn(B, 256, W, 2, device=dev)
 w = torch.randn(5, 13, 64, 2, device=dev) * 0.1
 b = torch.zeros(64, device=dev)
@@ -60,7 +74,7 @@ ws = torch.empty(L.modfx_cnn_layernorm_workspace_bytes(B, 64, 128, W), dtype=tor
 ms = timed(lambda: _lib.check(L.modfx_cnn_layernorm_f32(_vp(y), _vp(y), B, 64, 128, W, 0, 1e-5, 1, _vp(ws), _stream())))
 print(f"layer norm of (B, 128, 345, 64): {ms:.3f} ms  {2 * y.numel() * 4 / ms / 1e6:.0f} GB/s (read twice + write once: x1.5)")
 
-for prec in precisions + (["tf32x3"] if "tf32" in precisions else []):
+for prec in precisions + (["fp16", "tf32x3"] if "tf32" in precisions else []):
     net = Spectral2DCNN(in_ch=2, out_channels=[64] * 6, temp_dilations=DIL, pool_size=(2, 1), precision=prec).to(dev).eval()
     audio = torch.rand(B, 2, 88200, device=dev) - 0.5
     ms = timed(lambda: net(audio), n=3)

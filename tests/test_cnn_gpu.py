@@ -5,6 +5,7 @@ mod_extraction.models.Spectral2DCNN itself) and the numpy oracle.
 Tolerances (written out because this is floating point):
 * float32 path, body fed with the reference's own log-mel: output <= 2e-5, latent <= 1e-4 (summation order only);
 * float32 path end to end (own log-mel kernel in front): output <= 2e-4, latent <= 1e-3;
+* float16 operand storage (precision="fp16"): the TF32 bars -- float16 keeps the same 11 significant bits;
 * TF32 tensor-core path: output <= 3e-3, latent <= 1e-2 -- TF32 operands carry 10 mantissa bits; the oracle with
   TF32-rounded operands is itself 6e-4 / 1.8e-3 from the float32 reference.  A single tensor-core layer agrees
   with the CUDA-core kernel on identical TF32 operands to 1e-4 (measured 5e-5: the MMA's float32 accumulation is
@@ -196,6 +197,52 @@ def test_conv_tf32x3_vs_float32_oracle(dil, H, W, B):
     assert maxdiff(y1.cpu().numpy(), ref) > 2.0 * err3  # the plain TF32 result is visibly coarser on the same data
 
 
+@pytest.mark.parametrize("dil,H,W,B", [(1, 4, 33, 2), (1, 2, 128, 1), (2, 6, 130, 2), (4, 8, 345, 2), (16, 8, 345, 3), (8, 16, 345, 1)])
+def test_conv_fp16_operands_vs_fp32_kernel(dil, H, W, B):
+    """float16 operand storage on the tensor cores (K = 16 per MMA, one 128-byte panel per tap) against the CUDA-core
+    kernel fed the same float16-rounded values as float32: only the accumulation order differs."""
+    from mod_extraction_b200 import _lib
+    from mod_extraction_b200.models import _stream, _vp
+    L = _lib.lib()
+    rng = np.random.RandomState(400 + dil + W)
+    x = rng.standard_normal((B, 64, H, W)).astype(np.float32)
+    w = (rng.standard_normal((64, 64, 5, 13)) / math.sqrt(64 * 65)).astype(np.float32)
+    bias = rng.uniform(-0.2, 0.2, 64).astype(np.float32)
+    slope = rng.uniform(0.05, 0.4, 64).astype(np.float32)
+    xh = torch.from_numpy(x).to(DEV).permute(0, 2, 3, 1).contiguous().to(torch.float16)
+    wh = torch.from_numpy(w).to(DEV).permute(2, 3, 0, 1).contiguous().to(torch.float16)
+    bd, sd = torch.from_numpy(bias).to(DEV), torch.from_numpy(slope).to(DEV)
+    y_tc = torch.full((B, H // 2, W, 64), float("nan"), device=DEV)
+    y_cc = torch.empty((B, H // 2, W, 64), device=DEV)
+    _lib.check(L.modfx_cnn_conv_pool_prelu_f16_f32(_vp(xh), _vp(y_tc), B, H, W, dil, _vp(wh), _vp(bd), _vp(sd), _stream()))
+    xf, wf = xh.float(), wh.float()
+    _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(xf), _vp(y_cc), B, H, W, 64, 64, 5, 13, dil, _vp(wf), _vp(bd), _vp(sd),
+                                               _lib.CNN_FP32, _stream()))
+    torch.cuda.synchronize()
+    got = y_tc.cpu().numpy()
+    assert np.isfinite(got).all(), "tensor-core kernel left outputs unwritten"
+    assert maxdiff(got, y_cc.cpu().numpy()) <= 1e-4
+
+
+def test_layernorm_float16_output():
+    from mod_extraction_b200 import _lib
+    from mod_extraction_b200.models import _stream, _vp
+    from oracle import oracle
+    L = _lib.lib()
+    rng = np.random.RandomState(9)
+    B, C, H, W = 2, 64, 16, 345
+    x = (rng.standard_normal((B, C, H, W)) * 2.0 + 0.5).astype(np.float32)
+    ref = oracle.layer_norm_2d(x).transpose(0, 2, 3, 1).astype(np.float16)
+    xl = torch.from_numpy(x).to(DEV).permute(0, 2, 3, 1).contiguous()
+    y = torch.empty((B, H, W, C), dtype=torch.float16, device=DEV)
+    ws = torch.empty(L.modfx_cnn_layernorm_workspace_bytes(B, C, H, W), dtype=torch.uint8, device=DEV)
+    _lib.check(L.modfx_cnn_layernorm_f32(_vp(xl), _vp(y), B, C, H, W, 0, 1e-5, 3, _vp(ws), _stream()))
+    got = y.cpu().numpy()
+    # identical up to the float32 -> float16 rounding boundary (one float16 ulp where the float32 values differ by 1e-6)
+    assert maxdiff(got.astype(np.float32), ref.astype(np.float32)) <= 4e-3
+    assert (got == ref).mean() >= 0.995
+
+
 def test_head_vs_oracle():
     from mod_extraction_b200 import _lib
     from mod_extraction_b200.models import _stream, _vp
@@ -245,7 +292,7 @@ def test_body_tf32_on_reference_logmel_small():
     assert maxdiff(lat.cpu().numpy(), lo) <= 2e-3
 
 
-@pytest.mark.parametrize("precision,tol_y,tol_lat", [("fp32", 2e-4, 1e-3), ("tf32", 3e-3, 1e-2)])
+@pytest.mark.parametrize("precision,tol_y,tol_lat", [("fp32", 2e-4, 1e-3), ("tf32", 3e-3, 1e-2), ("fp16", 3e-3, 1e-2)])
 def test_end_to_end_small(precision, tol_y, tol_lat):
     g = golden("cnn")
     net, _ = make_net(8192, 64, 7, precision, fb=g["small_fb"])
@@ -266,7 +313,8 @@ def test_training_forward_replays_specaugment_draws():
     assert maxdiff(g["train_y"], g["small_y"]) > 1e-3          # the masks did change the result
 
 
-@pytest.mark.parametrize("precision,tol_y,tol_lat", [("fp32", 2e-4, 1e-3), ("tf32x3", 2e-4, 1e-3), ("tf32", 3e-3, 1e-2)])
+@pytest.mark.parametrize("precision,tol_y,tol_lat", [("fp32", 2e-4, 1e-3), ("tf32x3", 2e-4, 1e-3), ("tf32", 3e-3, 1e-2),
+                                                     ("fp16", 3e-3, 1e-2)])
 def test_end_to_end_shipped_shape(precision, tol_y, tol_lat):
     """configs/models/spectral_2dcnn.yml on 2 s clips: (2, 2, 88200) -> (2, 1, 345), (2, 64, 345)."""
     g = golden("cnn")
