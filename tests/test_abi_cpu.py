@@ -94,7 +94,6 @@ def test_cnn_entry_points_validate_before_touching_the_gpu():
     assert L.modfx_cnn_conv_pool_prelu_f32(p, q, 1, 3, 4, 64, 64, 5, 13, 1, p, p, p, 0, nul) == -2            # odd H
     assert L.modfx_cnn_conv_pool_prelu_f32(p, q, 1, 2, 4, 64, 64, 5, 13, 32, p, p, p, 0, nul) == -2           # dilation 32
     assert L.modfx_cnn_conv_pool_prelu_f32(p, q, 0, 2, 4, 64, 64, 5, 13, 1, p, p, p, 1, nul) == 0             # empty batch
-    assert b"5x13" in L.modfx_last_error() or True
     assert L.modfx_cnn_conv_pool_prelu_tf32x3_f32(p, nul, q, 1, 2, 4, 1, p, p, p, p, nul) == -1
     assert L.modfx_cnn_layernorm_f32(p, p, 1, 2, 4, 4, 1, 1e-5, 0, p, nul) == -1                               # NCHW in place
     assert L.modfx_cnn_layernorm_f32(p, q, 1, 3, 4, 4, 0, 1e-5, 0, p, nul) == -2                               # 3 does not divide 256
