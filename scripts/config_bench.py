@@ -1,4 +1,5 @@
 """Device-resident timings of the other BASELINE.json configurations (the contract bench.py measures config 4):
+  config 1  flanger, one 2 s clip, 2 Hz triangle LFO (the case the reference runs on a CPU in 9.3 s)
   config 2  phaser, 256 x 88 200, random-phase / rate cosine LFO (the ground-truth LFO of datasets.py:442 included)
   config 3  chorus + flanger, 1024 x 88 200, quasi-periodic and distorted control-rate LFOs (LFO generation timed apart)
   config 5  60 s clips x 512: flanger, chorus, phaser (+ the log-mel of one 60 s batch)
@@ -20,7 +21,7 @@ from mod_extraction_b200.phaser import Phaser                         # noqa: E4
 dev = torch.device("cuda", 0)
 SR = 44100
 PEAK = 6547.8
-which = [int(a) for a in sys.argv[1:]] or [2, 3, 5]
+which = [int(a) for a in sys.argv[1:]] or [1, 2, 3, 5]
 SHAPES6 = ["cos", "tri", "rect_cos", "inv_rect_cos", "saw", "rsaw"]
 
 
@@ -58,6 +59,20 @@ def white(B, N, seed):
 rng = np.random.RandomState(43)
 U = lambda B, lo, hi: torch.from_numpy(rng.uniform(lo, hi, B).astype(np.float32)).to(dev)
 LU = lambda B, lo, hi: torch.from_numpy(np.exp(rng.uniform(math.log(lo), math.log(hi), B)).astype(np.float32)).to(dev)
+
+if 1 in which:
+    # config 1: the reference's own CPU-runnable case (9.3 s in fx.py's python loop): one 2 s clip, flanger, 2 Hz triangle
+    B, N = 1, 88200
+    x = white(B, N, 42)
+    fl1 = MonoFlangerChorusModule(B, 1, N, SR, 1.0, 10.0, check_ranges=False)
+    lo = M.make_mod_signal_batch(882, 441.0, [2.0], [0.0], ["tri"])
+    out1 = torch.empty_like(x)
+    report("config 1: flanger 1 x 2 s, control-rate LFO in", B, N, timed(lambda: fl1.forward_control_rate(x, lo, 0.5, 1.0, 1.0, 1.0, 1.0, out=out1)), 8)
+    x_cpu, lo_cpu = x.cpu(), lo.cpu()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        y_cpu = fl1.forward_control_rate(x_cpu, lo_cpu, 0.5, 1.0, 1.0, 1.0, 1.0)
+    print(f"          the same through the CPU-tensor drop-in call (H2D + kernel + D2H + sync): {(time.perf_counter() - t0) / 5 * 1e3:.3f} ms")
 
 if 2 in which:
     B, N = 256, 88200
