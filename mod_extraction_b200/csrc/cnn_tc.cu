@@ -44,9 +44,14 @@ template <bool kHalf>
 struct Fmt {
     static constexpr int kPanels = kHalf ? 1 : 2;
     static constexpr int kChanPerPanel = kC / kPanels;
-    static constexpr int kStageA = kPanels * kPanelA;           // 32 KB / 16 KB
+    static constexpr int kRowBytes = kPanels * kPanelA;         // one input row of the tile: 32 KB / 16 KB
+    // input rows per pipeline stage.  With float16 operands a row is only ~210 cycles of tensor-pipe time per issuer,
+    // less than the issuer's own per-stage work (barrier waits, election, commits): two rows share one stage
+    // (a CTA's live input rows always come in an even number: 8 conv rows + 4 halo rows - 0 / 2 / 4 outside the image)
+    static constexpr int kRowsPerStage = kHalf ? 2 : 1;
+    static constexpr int kStageA = kRowsPerStage * kRowBytes;   // 32 KB either way
     static constexpr int kBytesB = kPanels * kPanelB;           // 80 KB / 40 KB
-    static constexpr int kAStages = kHalf ? 8 : 4;              // power of two; 128 KB of A in flight either way
+    static constexpr int kAStages = 4;                          // power of two; 128 KB of A in flight
     static constexpr int kNumBars = 2 * kAStages + 2 * kKH + 1;
     static constexpr int kSmemBytes = kAStages * kStageA + kBytesB + 1024 /* alignment slack */ + 8 * kNumBars + 16;
     static constexpr uint32_t kFormat = kHalf ? 0u : 2u;        // instruction descriptor: F16 = 0, TF32 = 2
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
     if (warp == 0) {
         // ===== A producer (whole warp walks the loop, one elected lane issues): a 128-frame x 64-channel box per
         // (kw, live input row) =====
-        int it = 0;
+        int it = 0, sub = 0;                                        // stage counter, row inside the stage
         for (int v = 0; v < n_pass * kKW; ++v) {                     // v = pass * 13 + kw
             const int pass = v / kKW, kw = v - pass * kKW;
             const CUtensorMap* tmx = &tm.x[pass == 2 ? 1 : 0];      // passes: hi*hi, hi*lo, lo*hi
@@ -238,17 +243,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
             for (int r = 0; r < kInRows; ++r) {
                 if (!plan.row_live(r)) continue;
                 const int s = it % kAStages;
-                mbar_wait(bar_aempty + 8 * s, (((uint32_t)(it / kAStages)) & 1u) ^ 1u);
+                if (sub == 0) mbar_wait(bar_aempty + 8 * s, (((uint32_t)(it / kAStages)) & 1u) ^ 1u);
                 if (elect_one()) {
                     const uint32_t full = bar_afull + 8 * s;
-                    const uint32_t st = a_base + s * kStageA;
-                    mbar_expect_tx(full, kStageA);
+                    const uint32_t st = a_base + s * kStageA + sub * F::kRowBytes;
+                    if (sub == 0) mbar_expect_tx(full, kStageA);
 #pragma unroll
                     for (int p = 0; p < F::kPanels; ++p)
                         tma_load_4d(st + p * kPanelA, tmx, full, p * F::kChanPerPanel, wx, plan.h0 - kKH / 2 + r, b);
                 }
                 __syncwarp();
-                ++it;
+                if (++sub == F::kRowsPerStage) {
+                    sub = 0;
+                    ++it;
+                }
             }
         }
     } else if (warp == 2) {
@@ -300,8 +308,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
                 if (f <= l && l == r) free_b[r] |= 1u << kh;
             }
         }
-        int it = 0, last_committed = -1;                           // stages whose A slot has been released: 0 .. last_committed
-        constexpr int kCommitEvery = kAStages / 4;                  // 1 (float32 operands, 4 slots) / 2 (float16, 8 slots)
+        int it = 0, sub = 0;                                        // stage counter, row inside the stage
+        uint32_t free_pending = 0;                                  // weight slots to release at the end of the stage
 #pragma unroll 1
         for (int v = 0; v < n_pass * kKW; ++v) {                     // v = pass * 13 + kw: the weight ring turns once per v
             const uint32_t b_par = (uint32_t)v & 1u;
@@ -315,10 +323,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
                     if ((wait_b[r] >> kh) & 1u) mbar_wait(bar_bfull + 8 * (kKH - 1 - kh), b_par);
                 // (waited for even when this issuer has no accumulator under the row: it keeps the two issuers within
                 // one ring revolution of each other, which the two-arrival "empty" barriers rely on)
-                mbar_wait(bar_afull + 8 * s, ((uint32_t)(it / kAStages)) & 1u);
+                if (sub == 0) mbar_wait(bar_afull + 8 * s, ((uint32_t)(it / kAStages)) & 1u);
                 if (run_n[r] > 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_lo = umma_desc_lo(a_base) + s * (kStageA >> 4);
+                    const uint32_t a_lo = umma_desc_lo(a_base) + s * (kStageA >> 4) + sub * (F::kRowBytes >> 4);
                     // at the very first tap a fresh accumulator overwrites while its neighbours already add: split the run there
                     int a = run_a[r];
                     int left = run_n[r];
@@ -346,28 +354,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
                 }
                 // accumulators r - kh_hi .. r - kh_lo (either issuer's) have been written once this row is through
                 started |= ((2u << (r - plan.kh_lo(r))) - 1u) & ~((1u << (r - plan.kh_hi(r))) - 1u);
-                // A slots are released kCommitEvery at a time: every tcgen05.commit is a drain point for this thread's
-                // MMA stream (measured: 36 commits cost 3.8 k of 16 k cycles per kw), so they are issued in bursts
-                if (((it + 1) & (kCommitEvery - 1)) == 0 || free_b[r] != 0) {
+                free_pending |= free_b[r];
+                if (++sub == F::kRowsPerStage) {
+                    // end of the stage: its A slot, and the weight slots whose last reader was in it, go back to the
+                    // producers once this issuer's MMAs have read them
                     if (elect_one()) {
-#pragma unroll
-                        for (int back = kCommitEvery - 1; back >= 0; --back)
-                            if (it - back > last_committed)
-                                umma_commit(bar_aempty + 8 * ((it - back) & (kAStages - 1)));
+                        umma_commit(bar_aempty + 8 * s);
 #pragma unroll
                         for (int kh = 0; kh < kKH; ++kh)
-                            if ((free_b[r] >> kh) & 1u) umma_commit(bar_bempty + 8 * (kKH - 1 - kh));
+                            if ((free_pending >> kh) & 1u) umma_commit(bar_bempty + 8 * (kKH - 1 - kh));
                     }
                     __syncwarp();
-                    last_committed = it;
+                    free_pending = 0;
+                    sub = 0;
+                    ++it;
                 }
-                ++it;
             }
         }
-        if (elect_one()) {
-            for (int j = last_committed + 1; j < it; ++j) umma_commit(bar_aempty + 8 * (j & (kAStages - 1)));
-            umma_commit(bar_acc);                                   // this issuer's accumulators are complete
-        }
+        if (elect_one()) umma_commit(bar_acc);                      // this issuer's accumulators are complete
         __syncwarp();
     } else {
         // ===== epilogue: lane = frame, column = output channel; conv rows 2 p and 2 p + 1 pool into output row p =====
