@@ -97,8 +97,20 @@ class InterwovenRenderer:
             st.wait_event(start)
         fc_keys = ("feedback", "min_delay_width", "width", "depth", "mix")
         ph_keys = ("rate_hz", "depth", "centre_frequency_hz", "feedback", "mix")
-        for lo in range(0, B, chunk):
-            hi = min(B, lo + chunk)
+        # chunk schedule: a short first and last chunk keep the part of the pipeline that cannot overlap (the first
+        # H2D copy, the last D2H copy) small; everything in between moves `chunk` examples at a time
+        edges, lo = [], 0
+        short = max(1, chunk // 4)
+        while lo < B:
+            left = B - lo
+            size = short if (lo == 0 and B > 2 * chunk) else (left if left <= chunk + short else chunk)
+            if lo > 0 and left <= chunk + short and left > short and B > 2 * chunk:
+                edges.append((lo, lo + left - short))
+                lo += left - short
+                size = short
+            edges.append((lo, lo + size))
+            lo += size
+        for lo, hi in edges:
             with torch.cuda.stream(s_in):
                 dry_d[lo:hi].copy_(dry_h[lo:hi], non_blocking=True)
                 m = mod_lo_h[lo:hi].to(self.device, non_blocking=True)
