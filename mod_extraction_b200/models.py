@@ -139,6 +139,8 @@ class MelSpectrogram(nn.Module):
         if out is None:
             out = torch.empty(lead + (self.n_mels, nf), device=x.device, dtype=torch.float32)
         assert out.is_contiguous() and out.numel() == R * self.n_mels * nf
+        if R == 0:                      # empty batch: nothing to launch (and no device pointer to pass)
+            return out
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().modfx_logmel_f32(
@@ -293,6 +295,9 @@ class Spectral2DCNN(nn.Module):
         logmel = logmel.detach().float().contiguous()
         B, C, H, W = logmel.shape
         assert C == self.in_ch and H == self.n_mels
+        if B == 0:
+            return (torch.empty((0, self.latent_dim, W), dtype=torch.float32, device=dev),
+                    torch.empty((0, self.out_channels[-1], W), dtype=torch.float32, device=dev))
         if B > self.max_chunk:                    # examples are independent: bound the activation memory
             outs = [self.forward_features(logmel[i:i + self.max_chunk]) for i in range(0, B, self.max_chunk)]
             return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)

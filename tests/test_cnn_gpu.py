@@ -391,3 +391,13 @@ def test_dry_audio_to_extracted_lfo_on_the_gpu():
     sm = modulations.smoothen(out.squeeze(1), 8)
     st = modulations.stretch_corners(out.squeeze(1), max_n_corners=16, smooth_n_frames=8)
     assert sm.shape == (B, 338) and st.is_cuda and bool(torch.isfinite(st[~torch.isnan(st)]).all())
+
+
+def test_empty_and_single_example_batches():
+    net, _ = make_net(8192, 64, 7, "tf32")
+    y, lat = net(torch.zeros((0, 2, 8192), device=DEV))
+    assert y.shape == (0, 1, 33) and lat.shape == (0, 64, 33)
+    x = t_white((1, 2, 8192), 5).to(DEV)
+    y1, l1 = net(x)
+    y3, l3 = net(torch.cat([x, x, x], 0))
+    assert y1.shape == (1, 1, 33) and torch.equal(y3[2:3], y1) and torch.equal(l3[0:1], l1)
