@@ -93,8 +93,17 @@ __global__ void __launch_bounds__(kLnThreads) ln_apply_kernel(const float* __res
     const int64_t e1 = min(e0 + kLnChunkElems, n);
     const float* xb = x + b * n;
     float* yb = y + b * n;
-    if (kNchw) {
-        // output element e = p * C + c reads x[c * P + p]; C is tiny here (2), so both sides stay coalesced enough
+    if (kNchw && C == 2) {
+        // the log-mel tensor of the front end: a thread takes one pixel, reads it from both planes (coalesced) and writes
+        // the interleaved pair
+        const float m0 = s_stat[0], r0 = s_stat[2], m1 = s_stat[1], r1 = s_stat[3];
+        for (int64_t p = e0 / 2 + tid; p < e1 / 2; p += kLnThreads) {
+            float a = (xb[p] - m0) * r0, c = (xb[P + p] - m1) * r1;
+            if (round) { a = round_tf32(a); c = round_tf32(c); }
+            *reinterpret_cast<float2*>(yb + 2 * p) = make_float2(a, c);
+        }
+    } else if (kNchw) {
+        // output element e = p * C + c reads x[c * P + p]
         for (int64_t e = e0 + tid; e < e1; e += kLnThreads) {
             const int64_t p = e / C;
             const int c = (int)(e - p * C);

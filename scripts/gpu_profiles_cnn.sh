@@ -1,7 +1,7 @@
 # ncu evidence for the extractor (N3): launch list of one forward at B = 32, full captures of both tcgen05 kernels.
 set -x
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 36 -c 18 --csv --log-file gpurun_out/launches_extractor.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 20 --csv --log-file gpurun_out/launches_extractor.csv \
     python scripts/prof_extractor.py 32 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tf32 -s 1 -c 1 -o gpurun_out/full_conv_tf32 \
     python scripts/prof_cnn.py 32 2 > /dev/null 2>&1
