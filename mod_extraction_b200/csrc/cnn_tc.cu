@@ -496,19 +496,27 @@ __global__ void __launch_bounds__(kThreads1, 2) conv1_tf32_kernel(const float* _
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_b) : "memory");
         }
-        int it = 0;
-        for (int r = 0; r < kInRows1; ++r) {
-            if (!row_live(r)) continue;
-            const int s = it & (kStages1 - 1);
+        // live rows are one contiguous range (dead rows lie above / below the image); the window of the NEXT row is
+        // fetched into registers before this row's tile is written, so the global-load latency hides behind the stores
+        int r_lo = 0, r_hi = -1;
+        for (int r = 0; r < kInRows1; ++r)
+            if (row_live(r)) { if (r_hi < 0) r_lo = r; r_hi = r; }
+        const int wl = w0 + tid - kKW / 2;                          // leftmost frame under this row's window
+        auto fetch = [&](int r, float2 (&v)[14]) {
             const float* xrow = x + (((int64_t)b * H + (h0 - kKH / 2 + r)) * W) * 2;
-            const int wl = w0 + tid - kKW / 2;                      // leftmost frame under this row's window
-            float2 v[14];
 #pragma unroll
             for (int kw = 0; kw < 14; ++kw) {
                 const int w = wl + kw;
                 v[kw] = (kw < kKW && w >= 0 && w < W) ? *reinterpret_cast<const float2*>(xrow + 2 * (int64_t)w)
                                                        : make_float2(0.0f, 0.0f);
             }
+        };
+        float2 v[14], vn[14];
+        if (r_hi >= r_lo) fetch(r_lo, v);
+        int it = 0;
+        for (int r = r_lo; r <= r_hi; ++r) {
+            const int s = it & (kStages1 - 1);
+            if (r < r_hi) fetch(r + 1, vn);
             mbar_wait(bar_empty + 8 * s, (((uint32_t)it >> 2) & 1u) ^ 1u);
             unsigned char* row = gen + s * kTileA1 + tid * 128;
 #pragma unroll
@@ -519,6 +527,8 @@ __global__ void __launch_bounds__(kThreads1, 2) conv1_tf32_kernel(const float* _
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+#pragma unroll
+            for (int kw = 0; kw < 14; ++kw) v[kw] = vn[kw];
             ++it;
         }
         // ===== epilogue =====
