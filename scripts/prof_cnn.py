@@ -1,4 +1,4 @@
-"""ncu target: a few launches of one conv + pool + PReLU layer.  python scripts/prof_cnn.py [B] [layer 2..6] [tf32|fp32]"""
+"""ncu target: a few launches of one conv + pool + PReLU layer.  python scripts/prof_cnn.py [B] [layer 2..6] [tf32|fp16|fp32]"""
 import os
 import sys
 
@@ -18,6 +18,12 @@ x = round_to_tf32(torch.randn(B, H, W, 64, device=dev))
 w = round_to_tf32(torch.randn(5, 13, 64, 64, device=dev) * 0.02)
 b = torch.zeros(64, device=dev)
 y = torch.empty(B, H // 2, W, 64, device=dev)
+if prec == "fp16":
+    xh, wh = x.half(), w.half()
+    for _ in range(3):
+        _lib.check(L.modfx_cnn_conv_pool_prelu_f16_f32(_vp(xh), _vp(y), B, H, W, DIL[layer - 1], _vp(wh), _vp(b), _vp(b), _stream()))
+    torch.cuda.synchronize()
+    sys.exit(0)
 for _ in range(3):
     _lib.check(L.modfx_cnn_conv_pool_prelu_f32(_vp(x), _vp(y), B, H, W, 64, 64, 5, 13, DIL[layer - 1], _vp(w), _vp(b), _vp(b),
                                                _lib.CNN_TF32 if prec == "tf32" else _lib.CNN_FP32, _stream()))
