@@ -391,38 +391,43 @@ def main():
                        "log-mel mean out, chunks pipelined over copy/compute/copy streams; the (B,2,256,345) log-mel "
                        "tensor stays in HBM where the extractor consumes it"}
 
+    checksum = float(wet.double().abs().mean().item())          # of the rendered batch, before any side measurement
     # ---------------- the consumer of the step's log-mel tensor, reported beside the headline, not in it
     extractor = None
     if not args.no_extractor:
-        from mod_extraction_b200.models import Spectral2DCNN
-        Bx = min(args.extractor_batch, B)
-        feats = logmel[:Bx]
-        flops = 2.0 * 65 * 64 * 345 * (256 * 2 + 64 * (128 + 64 + 32 + 16 + 8)) * Bx      # the six convolutions
-        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
-        extractor = {"what": "Spectral2DCNN body on the log-mel of this step (6 x {layer norm, 5x13 conv + pool + PReLU on "
-                             "tcgen05}, head), random weights", "batch": Bx, "gpu_launches_per_forward": 19,
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops for float16 operands, half of it for TF32 (the driver "
-                                    "measures no TF32 figure)"}
-        for prec, peak in (("tf32", bf16_peak / 2.0), ("fp16", bf16_peak)):
-            net = Spectral2DCNN(in_ch=2, n_samples=N, sr=SR, out_channels=[64] * 6, temp_dilations=[1, 1, 2, 4, 8, 16],
-                                pool_size=(2, 1), precision=prec).to(dev).eval()
-            for _ in range(2):
-                net.forward_features(feats)
-            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 3
-            x0.record()
-            for _ in range(reps):
-                out_x, _ = net.forward_features(feats)
-            x1.record()
-            torch.cuda.synchronize()
-            ms_x = x0.elapsed_time(x1) / reps
-            extractor[prec] = {"ms": ms_x, "audio_s_per_s": Bx * (N / SR) / (ms_x * 1e-3),
-                               "conv_tflops": flops / (ms_x * 1e-3) / 1e12, "peak_tflops": peak,
-                               "frac_of_peak": flops / (ms_x * 1e-3) / 1e12 / peak, "output_mean": float(out_x.mean().item())}
-            del net
+        try:
+            from mod_extraction_b200.models import Spectral2DCNN
+            Bx = min(args.extractor_batch, B)
+            feats = logmel[:Bx]
+            flops = 2.0 * 65 * 64 * 345 * (256 * 2 + 64 * (128 + 64 + 32 + 16 + 8)) * Bx      # the six convolutions
+            bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+            extractor = {"what": "Spectral2DCNN body on the log-mel of this step (6 x {layer norm, 5x13 conv + pool + PReLU on "
+                                 "tcgen05}, head), random weights", "batch": Bx, "gpu_launches_per_forward": 19,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops for float16 operands, half of it for TF32 (the driver "
+                                        "measures no TF32 figure)"}
+            for prec, peak in (("tf32", bf16_peak / 2.0), ("fp16", bf16_peak)):
+                torch.manual_seed(1234)                 # the same random weights for both operand formats
+                net = Spectral2DCNN(in_ch=2, n_samples=N, sr=SR, out_channels=[64] * 6, temp_dilations=[1, 1, 2, 4, 8, 16],
+                                    pool_size=(2, 1), precision=prec).to(dev).eval()
+                for _ in range(2):
+                    net.forward_features(feats)
+                x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 3
+                x0.record()
+                for _ in range(reps):
+                    out_x, _ = net.forward_features(feats)
+                x1.record()
+                torch.cuda.synchronize()
+                ms_x = x0.elapsed_time(x1) / reps
+                extractor[prec] = {"ms": ms_x, "audio_s_per_s": Bx * (N / SR) / (ms_x * 1e-3),
+                                   "conv_tflops": flops / (ms_x * 1e-3) / 1e12, "peak_tflops": peak,
+                                   "frac_of_peak": flops / (ms_x * 1e-3) / 1e12 / peak, "output_mean": float(out_x.mean().item())}
+                del net
+
+        except Exception as exc:      # a side measurement must never take the headline line down with it
+            extractor = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---------------- final gather of per-rank metrics (the only collective, outside the timed region)
-    checksum = float(wet.double().abs().mean().item())
     gather_ms = None
     if world > 1:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
