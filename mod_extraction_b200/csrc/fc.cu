@@ -15,6 +15,8 @@
 // arithmetic of a sample, so the result is identical in all modes.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace modfx {
 namespace {
 
@@ -49,6 +51,7 @@ struct FcArgs {
     const int32_t* index;
     int n_items;
     int wide;                       // 1: examples that qualify for fc_wide_kernel are rendered there and skipped here
+    long long* stats;               // MODFX_FC_STATS builds only: per-CTA schedule counters of fc_cta_kernel
 };
 
 enum ModMode { kAudioRate = 0, kControlRate = 1, kDirectLfo = 2 };
@@ -558,6 +561,535 @@ __global__ void __launch_bounds__(kWarp) fc_kernel(const FcArgs a) {
     cp_async_wait<0>();
 }
 
+// ---- CTA per delay line, warp-specialised: the latency-oriented schedule (DESIGN.md "E1") ------------------
+// The one-warp kernel above spends ~1400 cycles per 128-sample tile because one warp does everything in turn: index
+// arithmetic, x100 upsample, taps, the recurrence, the mix.  Only the recurrence v[n] = x[n] + fb * it[n] is
+// sequential; everything else is a function of n alone.  Here a CTA of 4 warps owns one delay line:
+//   * 3 PRODUCER warps run ahead, a 128-sample tile each in turn: they fill a ring of tile slots with
+//     {x, fraction, 1 - fraction, shared-memory indices of the two taps} per sample (fx.py:95-102 + the upsample of
+//     util.py:15-29) and a dependency summary {min / max tap distance, slack} per 32-sample block; the same warp later
+//     takes the interpolated values the consumer left in the slot and does fx.py:115-118 + the store;
+//   * 1 CONSUMER warp only resolves the recurrence -- a single warp issues at most one instruction per cycle, so what it
+//     executes per sample is kept to the loads of the two taps, the five float operations of fx.py:113-114 and two
+//     stores: 128 samples in one shot when no tap falls inside the tile, four one-wave blocks when no tap falls inside
+//     its own block, else per block one wave / waves / a register-history serial run.
+// Hand-off through two kinds of shared-memory counters (tiles filled per producer, tiles done by the consumer) written
+// with st.release and polled with ld.acquire; both sides cache what they last read, so in steady state a tile costs
+// no synchronisation at all (an mbarrier try_wait costs ~90 cycles even when the phase is already complete).
+// A slot is refilled by the warp that drained it.  The consumer role rotates over the warp index with the CTA index
+// (warp w runs on scheduler w % 4: otherwise every consumer of an SM would share one scheduler).
+// Same per-sample arithmetic => same bits.
+constexpr int kCtaProd = 3;
+constexpr int kCtaThreads = (kCtaProd + 1) * kWarp;     // 128
+constexpr int kNT = 2 * kCtaProd;                       // tile slots in flight (two per producer)
+constexpr int kXDepth = 4;                              // dry-audio tiles in flight per producer warp (cp.async)
+constexpr int kLoSmemMax = 2048;                        // in-kernel synthesised control rows up to this many points
+constexpr int kSlotFloats = 4 * kTile + kTile + 8;      // float4 coef[128] | it[128] | slack of the four blocks, schedule codes
+constexpr int kSerialK = 8;                             // register-history serial runs cover tap distances up to this (+1)
+
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;\n" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+// Lock-step serial run over `ngroups` groups of 4 consecutive samples (whole 32-sample blocks) whose tap distances are
+// all K or K+1.  A pre-pass (one sample per lane, see serial_records) has turned the per-sample records into
+// {x, cA, cB, cC}: it = cA * v[n-K+1] + (cB * v[n-K] + cC * v[n-K-1]) with (cA, cB, cC) = (fraction, 1 - fraction, 0)
+// for a tap distance of K and (0, fraction, 1 - fraction) for K+1 -- the product with the zero coefficient adds an
+// exact zero, so the sum has the bits of fx.py:113 -- and for K = 1, where the far tap of a sub-sample delay is the
+// stale sample M back, {x, cA, cB, S}: it = cA * v[n-1] + (cB * v[n-2] + S), S = fraction * stale or 0.  No select is
+// left in the loop: the previous sample enters through one multiply, so a sample costs the four dependent float
+// operations of fx.py:113-114.  A real loop (the body stays in the instruction cache); the records of the next group
+// are pulled into registers ahead of the dependent chain, the taps come from history REGISTERS, results leave as two
+// 16-byte stores per group from one lane.
+#ifdef MODFX_FC_STATS
+}  // namespace
+__device__ unsigned long long g_serial_stats[4];     // calls, cycles inside the sample loop, cycles of the whole call
+namespace {
+#endif
+
+template <int K>
+__device__ __noinline__ void serial_run(float* __restrict__ ring, int mask, int nb, const float4* __restrict__ coef,
+                                        float fb, float* __restrict__ it_out, int lane, int ngroups) {
+#ifdef MODFX_FC_STATS
+    const long long sr_t0 = clock64();
+#endif
+    // w[3 + j] = v[g0 - j] for j >= 1 (history before the current group of 4 samples), w[3 - u] = sample u of the group:
+    // the tap of sample u at distance d is w[3 - u + d] whether it lies before the group or inside it.
+    float w[K + 5];
+#pragma unroll
+    for (int j = 1; j <= K + 1; ++j) w[3 + j] = ring[(nb - j) & mask];
+    float4* dst = reinterpret_cast<float4*>(ring + (nb & mask));    // tiles are 128-aligned, the ring a multiple of 128
+    float4* ito = reinterpret_cast<float4*>(it_out);
+    float4 cur[4], nxt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cur[u] = coef[u];
+#ifdef MODFX_FC_STATS
+    const long long sr_t1 = clock64();
+#endif
+#pragma unroll 1
+    for (int g = 0; g < ngroups; ++g) {
+        const int gn = min(g + 1, ngroups - 1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nxt[u] = coef[4 * gn + u];
+        float its[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 cf = cur[u];
+            const float far = (K == 1) ? cf.w : __fmul_rn(cf.w, w[3 - u + K + 1]);
+            const float it = __fadd_rn(__fmul_rn(cf.y, w[3 - u + (K == 1 ? 1 : K - 1)]),
+                                       __fadd_rn(__fmul_rn(cf.z, w[3 - u + (K == 1 ? 2 : K)]), far));     // fx.py:113
+            its[u] = it;
+            w[3 - u] = __fadd_rn(cf.x, __fmul_rn(fb, it));                                                 // fx.py:114
+        }
+        if (lane == 0) {            // every lane holds the same values: one lane stores
+            dst[g] = make_float4(w[3], w[2], w[1], w[0]);
+            ito[g] = make_float4(its[0], its[1], its[2], its[3]);
+        }
+#pragma unroll
+        for (int k = K + 4; k >= 4; --k) w[k] = w[k - 4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+    }
+#ifdef MODFX_FC_STATS
+    if (lane == 0) {
+        const long long sr_t2 = clock64();
+        atomicAdd(&g_serial_stats[0], 1ull);
+        atomicAdd(&g_serial_stats[1], (unsigned long long)ngroups);
+        atomicAdd(&g_serial_stats[2], (unsigned long long)(sr_t2 - sr_t0));
+        atomicAdd(&g_serial_stats[3], (unsigned long long)(sr_t2 - sr_t1));
+    }
+#endif
+}
+
+template <int MODE, bool SYNTH>
+__global__ void __launch_bounds__(kCtaThreads) fc_cta_kernel(const FcArgs a, int lo_smem) {
+    extern __shared__ __align__(16) float smem[];
+    int* filled = reinterpret_cast<int*>(smem);                            // [kCtaProd] tiles filled by producer p
+    int* done = filled + 4;                                                // tiles resolved by the consumer
+    float* red = smem + 8;                                                 // [8]
+    float* slots = smem + 16;                                              // [kNT][kSlotFloats]
+    float* xstage = slots + kNT * kSlotFloats;                             // [kCtaProd][kXDepth][128] dry audio in flight
+    float* mstage = xstage + kCtaProd * kXDepth * kTile;                   // same for an audio-rate mod_sig
+    float* lo_s = mstage + ((MODE == kAudioRate) ? kCtaProd * kXDepth * kTile : 0);   // [lo_smem] synthesised control row
+    float* ring = lo_s + lo_smem;                                          // written samples, indexed by time & mask
+    const int ring_w = (int)(ring - smem);                                 // word index of the ring inside smem[]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int item = blockIdx.x / a.C;
+    const int ch = blockIdx.x - item * a.C;
+    const int b = a.index ? a.index[item] : item;
+    const int N = a.N;
+    const Coef c = make_coef(a, b);
+    const int mask = c.mask;
+    const float* lo = (MODE == kControlRate) ? (SYNTH ? lo_s : a.mod + (int64_t)b * a.n_lo) : nullptr;
+
+    if (MODE == kControlRate && !SYNTH && a.wide) {
+        // examples whose every tap lies more than a wide tile back were rendered by fc_wide_kernel (same predicate)
+        float mn = INFINITY, mx = -INFINITY;
+        for (int i = tid; i < a.n_lo; i += kCtaThreads) {
+            const float v = __ldg(lo + i);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+            if (!(v == v)) mx = INFINITY;
+        }
+        warp_minmax(mn, mx);
+        if (lane == 0) { red[warp] = mn; red[4 + warp] = mx; }
+        __syncthreads();
+        mn = fminf(fminf(red[0], red[1]), fminf(red[2], red[3]));
+        mx = fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]));
+        if (wide_pred(c, mn, mx)) return;                  // CTA-uniform
+    }
+    if (tid < 8) filled[tid] = 0;
+    for (int i = tid; i <= mask; i += kCtaThreads) ring[i] = 0.0f;                   // fx.py:92
+    if (MODE == kControlRate && SYNTH) {
+        const LfoDesc lfo = make_lfo_desc(a.lfo_freq[b], a.lfo_phase[b], a.lfo_shape[b], a.lfo_exp ? a.lfo_exp[b] : 1.0f, a.sr_lo);
+        for (int i = tid; i < a.n_lo; i += kCtaThreads) lo_s[i] = lfo_value(lfo, i);
+    }
+    __syncthreads();
+
+    const int ntiles = (N + kTile - 1) / kTile;
+    const float* xs = a.x + ((int64_t)b * a.C + ch) * (int64_t)N;
+    float* ys = a.y + ((int64_t)b * a.C + ch) * (int64_t)N;
+    const int cw = blockIdx.x & 3;                          // the consumer's warp index rotates with the CTA index
+
+    if (warp != cw) {
+        // ================================ producers ================================
+        const int p = (warp - cw - 1) & 3;                  // 0 .. 2
+        const float* ms = nullptr;
+        if (MODE == kAudioRate) ms = a.mod + (a.mod_has_ch ? ((int64_t)b * a.C + ch) : (int64_t)b) * (int64_t)N;
+        float* xq = xstage + p * kXDepth * kTile;
+        float* mq = mstage + p * kXDepth * kTile;
+        const bool coef_ok = (c.A >= 0.0f) && (c.D0 >= 0.0f) && (__fadd_rn(c.A, c.D0) <= c.Mf);
+        const int last_lo = a.n_lo - 1;
+        // dry audio (and the audio-rate mod_sig) of this warp's next kXDepth tiles travels through cp.async
+#pragma unroll
+        for (int d = 0; d < kXDepth - 1; ++d) {
+#pragma unroll
+            for (int k = 0; k < kSub; ++k) {
+                const int n = (p + d * kCtaProd) * kTile + k * kWarp + lane;
+                if (n < N) {
+                    cp_async_4(xq + d * kTile + k * kWarp + lane, xs + n, 4);
+                    if (MODE == kAudioRate) cp_async_4(mq + d * kTile + k * kWarp + lane, ms + n, 4);
+                }
+            }
+            cp_async_commit();
+        }
+        int wk[kSub];
+#pragma unroll
+        for (int k = 0; k < kSub; ++k) wk[k] = (p * kTile + k * kWarp + lane) % c.M;
+        const int wstep = (kCtaProd * kTile) % c.M;
+        int q = 0;                                          // stage of this warp's current tile
+        int done_seen = 0;
+#ifdef MODFX_FC_STATS
+        long long pr_cyc[4] = {0, 0, 0, 0};                 // wait for the consumer, epilogue, audio wait, fill
+        long long pr_t0 = clock64();
+#define PR_STAT(k) do { const long long t1_ = clock64(); pr_cyc[k] += t1_ - pr_t0; pr_t0 = t1_; } while (0)
+#else
+#define PR_STAT(k) do { } while (0)
+#endif
+        for (int t = p; t < ntiles + kNT; t += kCtaProd) {
+            float* slot = slots + (t % kNT) * kSlotFloats;
+            float4* cs = reinterpret_cast<float4*>(slot);
+            float* itb = slot + 4 * kTile;
+            int* meta = reinterpret_cast<int*>(slot + 5 * kTile);
+            if (t >= kNT) {
+                // ---- epilogue of tile t - kNT, which lived in this slot: fx.py:115-118 ----
+                const int td = t - kNT;
+                while (done_seen <= td) {
+                    done_seen = ld_acquire(done);
+                    if (done_seen <= td) __nanosleep(32);   // leave the issue slots to the warps that have work
+                }
+                PR_STAT(0);
+#pragma unroll
+                for (int k = 0; k < kSub; ++k) {
+                    const float x = cs[k * kWarp + lane].x;
+                    const float it = itb[k * kWarp + lane];
+                    const float o = __fadd_rn(x, __fmul_rn(c.depth, it));                       // fx.py:115
+                    const float r = __fadd_rn(__fmul_rn(c.omm, x), __fmul_rn(c.mix, o));        // fx.py:117
+                    const int nj = td * kTile + k * kWarp + lane;
+                    if (nj < N) ys[nj] = fminf(fmaxf(r, -1.0f), 1.0f);                          // fx.py:118
+                }
+                __syncwarp();
+                PR_STAT(1);
+            }
+            if (t < ntiles) {
+                {   // keep kXDepth - 1 tiles in flight
+                    int qs = q + kXDepth - 1;
+                    if (qs >= kXDepth) qs -= kXDepth;
+#pragma unroll
+                    for (int k = 0; k < kSub; ++k) {
+                        const int n = (t + (kXDepth - 1) * kCtaProd) * kTile + k * kWarp + lane;
+                        if (n < N) {
+                            cp_async_4(xq + qs * kTile + k * kWarp + lane, xs + n, 4);
+                            if (MODE == kAudioRate) cp_async_4(mq + qs * kTile + k * kWarp + lane, ms + n, 4);
+                        }
+                    }
+                    cp_async_commit();
+                }
+                cp_async_wait<kXDepth - 1>();               // every lane reads back only what it copied itself
+                PR_STAT(2);
+                // straight-line arithmetic for the four 32-sample blocks of the tile (independent chains interleave);
+                // the exact-remainder path of fc_index is taken afterwards for the whole tile if any sample needs it
+                float xv[kSub], mv[kSub], frv[kSub], omv[kSub];
+                int kpv[kSub];
+                bool bad = !coef_ok;
+#pragma unroll
+                for (int k = 0; k < kSub; ++k) {
+                    const int n = t * kTile + k * kWarp + lane;
+                    const bool mine = n < N;
+                    xv[k] = mine ? xq[q * kTile + k * kWarp + lane] : 0.0f;
+                    float m;
+                    if (MODE == kAudioRate) {
+                        m = mine ? mq[q * kTile + k * kWarp + lane] : 0.0f;
+                    } else {
+                        const float src = __fmul_rn(a.up_scale, (float)min(n, N - 1));          // util.py:15-29
+                        const int i0 = min((int)src, last_lo);
+                        const float l1 = __fsub_rn(src, (float)i0);
+                        const float l0 = __fsub_rn(1.0f, l1);
+                        const float m0 = SYNTH ? lo[i0] : __ldg(lo + i0);
+                        const float m1 = SYNTH ? lo[min(i0 + 1, last_lo)] : __ldg(lo + min(i0 + 1, last_lo));
+                        m = __fmaf_rn(l0, m0, __fmul_rn(l1, m1));
+                    }
+                    mv[k] = m;
+                    bad = bad || !(m >= 0.0f && m <= 1.0f);
+                    // 0 <= d <= M, so (w - d) + M lies in [0, 2M): the remainder is one conditional subtraction
+                    const float d = __fadd_rn(__fmul_rn(c.A, m), c.D0);                         // fx.py:98
+                    const float tt = __fadd_rn(__fsub_rn((float)wk[k], d), c.Mf);               // fx.py:99
+                    const float r = (tt >= c.Mf) ? __fsub_rn(tt, c.Mf) : tt;                    // % M
+                    const float pf = floorf(r);
+                    frv[k] = __fsub_rn(r, pf);                                                   // fx.py:100
+                    omv[k] = __fsub_rn(1.0f, frv[k]);
+                    int kp = wk[k] - min((int)pf, c.M - 1);                                      // fx.py:101
+                    if (kp <= 0) kp += c.M;
+                    kpv[k] = kp;
+                }
+                if (__any_sync(kFull, bad)) {
+#pragma unroll
+                    for (int k = 0; k < kSub; ++k) fc_index(mv[k], wk[k], c, frv[k], omv[k], kpv[k]);
+                }
+                int slk[kSub];
+#pragma unroll
+                for (int k = 0; k < kSub; ++k) {
+                    const int n = t * kTile + k * kWarp + lane;
+                    const int kp = kpv[k];
+                    // where the two taps live: word indices into smem[] (the consumer loads smem[ip], smem[iq])
+                    const int ip = ring_w + ((n - kp) & mask);
+                    const int iq = ring_w + ((n - kq_of(kp, c.M)) & mask);
+                    cs[k * kWarp + lane] = make_float4(xv[k], frv[k], omv[k], __int_as_float((ip << 16) | iq));
+                    // slack > 0: no sample of the block has a tap inside the block (near = min(kp, kq))
+                    slk[k] = __reduce_min_sync(kFull, (n < N) ? (max(kp - 1, 1) - lane) : 0x7fffffff);
+                    wk[k] += wstep;
+                    if (wk[k] >= c.M) wk[k] -= c.M;
+                }
+                // Blocks with a tap inside themselves (rare outside the low-delay stretches, where the producers idle
+                // anyway) are classified here, off the consumer's critical path: 1..kSerialK = every tap distance is
+                // K or K+1 (register-history serial run; the records are rewritten to the select-free form
+                // {x, cA, cB, cC} of serial_run), 14 = waves, 15 = generic serial run; 0 = no tap inside the block.
+                unsigned codes = 0;
+                if (min(min(slk[0], slk[1]), min(slk[2], slk[3])) <= 0) {
+#pragma unroll
+                    for (int k = 0; k < kSub; ++k) {
+                        if (slk[k] <= 0) {                  // warp-uniform
+                            const int nb = t * kTile + k * kWarp;
+                            const bool mine = nb + lane < N;
+                            const int kp = kpv[k];
+                            const int kmin = __reduce_min_sync(kFull, mine ? kp : 0x7fffffff);
+                            const int kmax = __reduce_max_sync(kFull, mine ? kp : 0);
+                            unsigned code;
+                            if (nb + kWarp <= N && kmax - kmin <= 1 && kmin <= kSerialK && c.M >= 2 * kWarp) {
+                                code = (unsigned)kmin;
+                                const bool sel = kp == kmin;        // tap distance K (else K + 1)
+                                float4 o;
+                                o.x = xv[k];
+                                if (kmin == 1) {    // taps (previous, stale M back) or (2 back, previous); the consumer
+                                    o.y = sel ? omv[k] : frv[k];    // multiplies .w by the stale sample before the run
+                                    o.z = sel ? 0.0f : omv[k];
+                                    o.w = sel ? frv[k] : 0.0f;
+                                } else {
+                                    o.y = sel ? frv[k] : 0.0f;
+                                    o.z = sel ? omv[k] : frv[k];
+                                    o.w = sel ? 0.0f : omv[k];
+                                }
+                                cs[k * kWarp + lane] = o;
+                            } else {
+                                code = (kmin >= 3) ? 14u : 15u;
+                            }
+                            codes |= code << (4 * k);
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    reinterpret_cast<int4*>(meta)[0] = make_int4(slk[0], slk[1], slk[2], slk[3]);
+                    meta[4] = (int)codes;
+                }
+                __syncwarp();
+                if (lane == 0) st_release(filled + p, t / kCtaProd + 1);
+                if (++q == kXDepth) q = 0;
+                PR_STAT(3);
+            }
+        }
+        cp_async_wait<0>();
+#ifdef MODFX_FC_STATS
+        if (lane == 0 && p == 0 && a.stats) {
+            long long* o = a.stats + (long long)gridDim.x * 12 + (long long)blockIdx.x * 4;
+            for (int k = 0; k < 4; ++k) o[k] = pr_cyc[k];
+        }
+#endif
+        return;
+    }
+
+    // ================================ consumer ================================
+#ifdef MODFX_FC_STATS
+    long long st_cnt[6] = {0, 0, 0, 0, 0, 0}, st_cyc[6] = {0, 0, 0, 0, 0, 0};   // wait, one-shot / 4 x one-wave tiles, wave1, serial, waves, generic
+    long long st_t0 = clock64();
+#define FC_STAT(k) do { const long long t1_ = clock64(); st_cnt[k]++; st_cyc[k] += t1_ - st_t0; st_t0 = t1_; } while (0)
+#else
+#define FC_STAT(k) do { } while (0)
+#endif
+    int avail = 0;                                          // tiles [0, avail) are known to be filled
+    int sl = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        while (t >= avail) {
+            const int f0 = ld_acquire(filled), f1 = ld_acquire(filled + 1), f2 = ld_acquire(filled + 2);
+            avail = min(min(kCtaProd * f0, kCtaProd * f1 + 1), kCtaProd * f2 + 2);
+        }
+        FC_STAT(0);
+        float* slot = slots + sl * kSlotFloats;
+        float4* cs = reinterpret_cast<float4*>(slot);
+        float* itb = slot + 4 * kTile;
+        const int4 sk4 = *reinterpret_cast<const int4*>(slot + 5 * kTile);
+        const int sk[kSub] = {sk4.x, sk4.y, sk4.z, sk4.w};
+        const int n0 = t * kTile;
+        const bool whole = n0 + kTile <= N;
+        bool shot = whole, waves1 = whole;                  // no tap inside the tile / inside its own block
+#pragma unroll
+        for (int j = 0; j < kSub; ++j) {
+            shot = shot && (sk[j] - j * kWarp > 0);
+            waves1 = waves1 && (sk[j] > 0);
+        }
+        if (waves1) {
+            float4 r[kSub];
+#pragma unroll
+            for (int j = 0; j < kSub; ++j) r[j] = cs[j * kWarp + lane];
+            float* wr = ring + ((n0 + lane) & mask);        // tiles are 128-aligned, the ring a multiple of 128
+            if (shot) {
+                // ---- no tap of these 128 samples falls inside them: one shot ----
+                float vp[kSub], vq[kSub];
+#pragma unroll
+                for (int j = 0; j < kSub; ++j) {
+                    const unsigned pk = __float_as_uint(r[j].w);
+                    vp[j] = smem[pk >> 16];
+                    vq[j] = smem[pk & 0xffffu];
+                }
+#pragma unroll
+                for (int j = 0; j < kSub; ++j) {
+                    const float it = __fadd_rn(__fmul_rn(r[j].y, vq[j]), __fmul_rn(r[j].z, vp[j]));    // fx.py:113
+                    wr[j * kWarp] = __fadd_rn(r[j].x, __fmul_rn(c.fb, it));                             // fx.py:114
+                    itb[j * kWarp + lane] = it;
+                }
+            } else {
+                // ---- no tap of a block falls inside that block: four waves, nothing but the taps in between ----
+#pragma unroll
+                for (int j = 0; j < kSub; ++j) {
+                    const unsigned pk = __float_as_uint(r[j].w);
+                    const float vp = smem[pk >> 16];
+                    const float vq = smem[pk & 0xffffu];
+                    const float it = __fadd_rn(__fmul_rn(r[j].y, vq), __fmul_rn(r[j].z, vp));           // fx.py:113
+                    wr[j * kWarp] = __fadd_rn(r[j].x, __fmul_rn(c.fb, it));                             // fx.py:114
+                    itb[j * kWarp + lane] = it;
+                    __syncwarp();
+                }
+            }
+            FC_STAT(1);
+        } else {
+            // ---- some block has a tap inside itself: the producer left a schedule code per block
+            const unsigned codes = (unsigned)reinterpret_cast<const int*>(slot + 5 * kTile)[4];
+            // (a rolled loop on purpose: four unrolled copies of the schedules below do not fit the instruction cache)
+            int j = 0;
+#pragma unroll 1
+            while (j < kSub) {
+                const unsigned code = (codes >> (4 * j)) & 15u;
+                const int nb = n0 + j * kWarp;
+                const int cnt = min(kWarp, N - nb);
+                if (cnt <= 0) break;
+                const int n = nb + lane;
+                const bool mine = lane < cnt;
+                if (code >= 1 && code <= (unsigned)kSerialK) {
+                    // ---- delays of K..K+1 samples: register-history serial run over this block and the blocks of the tile
+                    // that follow with the same K (records already in serial form) ----
+                    int L = 1;
+                    while (j + L < kSub && ((codes >> (4 * (j + L))) & 15u) == code) ++L;
+                    float4* cb = cs + j * kWarp;
+                    if (code == 1) {
+                        // far tap of a sub-sample delay: the stale sample M back, S = fraction * stale (fx.py:113)
+                        for (int l = 0; l < L; ++l) {
+                            float* wp = &cb[l * kWarp + lane].w;
+                            *wp = __fmul_rn(*wp, ring[(n + l * kWarp - c.M) & mask]);
+                        }
+                    }
+                    __syncwarp();
+                    float* ito = itb + j * kWarp;
+                    switch (code) {
+                        case 1: serial_run<1>(ring, mask, nb, cb, c.fb, ito, lane, 8 * L); break;
+                        case 2: serial_run<2>(ring, mask, nb, cb, c.fb, ito, lane, 8 * L); break;
+                        case 3: serial_run<3>(ring, mask, nb, cb, c.fb, ito, lane, 8 * L); break;
+                        case 4: serial_run<4>(ring, mask, nb, cb, c.fb, ito, lane, 8 * L); break;
+                        case 5: serial_run<5>(ring, mask, nb, cb, c.fb, ito, lane, 8 * L); break;
+                        case 6: serial_run<6>(ring, mask, nb, cb, c.fb, ito, lane, 8 * L); break;
+                        case 7: serial_run<7>(ring, mask, nb, cb, c.fb, ito, lane, 8 * L); break;
+                        default: serial_run<8>(ring, mask, nb, cb, c.fb, ito, lane, 8 * L); break;
+                    }
+                    __syncwarp();
+#ifdef MODFX_FC_STATS
+                    st_cnt[3] += L - 1;
+#endif
+                    FC_STAT(3);
+                    j += L;
+                    continue;
+                }
+                const float4 r = cs[j * kWarp + lane];
+                const unsigned pk = __float_as_uint(r.w);
+                const int ip = pk >> 16, iq = pk & 0xffffu;
+                float my_it = 0.0f;
+                if (code == 0) {
+                    // every sample depends only on samples before the block: one wave
+                    my_it = __fadd_rn(__fmul_rn(r.y, smem[iq]), __fmul_rn(r.z, smem[ip]));
+                    if (mine) ring[n & mask] = __fadd_rn(r.x, __fmul_rn(c.fb, my_it));
+                    itb[j * kWarp + lane] = my_it;
+                    __syncwarp();
+                    FC_STAT(2);
+                } else if (code == 14) {
+                    // waves of kmin - 1 consecutive samples: sample i depends on samples <= i - (kmin - 1).  Every lane
+                    // computes in every wave (no divergence); only the lanes of the wave keep and store their result.
+                    const int kp = (n - (ip - ring_w)) & mask;
+                    const int mn = __reduce_min_sync(kFull, mine ? kp : 0x7fffffff) - 1;
+                    for (int dn = 0; dn < cnt; dn += mn) {
+                        const float it = __fadd_rn(__fmul_rn(r.y, smem[iq]), __fmul_rn(r.z, smem[ip]));
+                        const float v = __fadd_rn(r.x, __fmul_rn(c.fb, it));
+                        if (lane >= dn && lane < dn + mn && mine) {
+                            ring[n & mask] = v;
+                            my_it = it;
+                        }
+                        __syncwarp();
+                    }
+                    itb[j * kWarp + lane] = my_it;
+                    FC_STAT(4);
+                } else {
+                    // ---- anything else with a 1-2 sample delay in it: generic lock-step serial run; taps at
+                    // distance 1 and 2 come from registers, older taps are loaded two samples ahead ----
+                    const int kp = (n - (ip - ring_w)) & mask;
+                    float p1 = ring[(nb - 1) & mask];
+                    float p2 = ring[(nb - 2) & mask];
+                    int kpa = __shfl_sync(kFull, kp, 0);
+                    int kpb = __shfl_sync(kFull, kp, 1);
+                    float lpa = ring[(nb - kpa) & mask];
+                    float lqa = ring[(nb - kq_of(kpa, c.M)) & mask];
+                    float lpb = ring[(nb + 1 - kpb) & mask];
+                    float lqb = ring[(nb + 1 - kq_of(kpb, c.M)) & mask];
+#pragma unroll 1
+                    for (int i = 0; i < cnt; ++i) {
+                        const int kpc = __shfl_sync(kFull, kp, (i + 2) & 31);
+                        const float lpc = ring[(nb + i + 2 - kpc) & mask];
+                        const float lqc = ring[(nb + i + 2 - kq_of(kpc, c.M)) & mask];
+                        const float xi = __shfl_sync(kFull, r.x, i);
+                        const float fri = __shfl_sync(kFull, r.y, i);
+                        const float omi = __shfl_sync(kFull, r.z, i);
+                        const int kqa = kq_of(kpa, c.M);
+                        const float vp = (kpa == 1) ? p1 : ((kpa == 2) ? p2 : lpa);
+                        const float vq = (kqa == 1) ? p1 : ((kqa == 2) ? p2 : lqa);
+                        const float it = __fadd_rn(__fmul_rn(fri, vq), __fmul_rn(omi, vp));     // fx.py:113
+                        const float v = __fadd_rn(xi, __fmul_rn(c.fb, it));                      // fx.py:114
+                        if (lane == 0) ring[(nb + i) & mask] = v;    // every lane holds the same value: one lane stores
+                        __syncwarp();
+                        if (lane == i) my_it = it;
+                        p2 = p1; p1 = v;
+                        kpa = kpb; lpa = lpb; lqa = lqb;
+                        kpb = kpc; lpb = lpc; lqb = lqc;
+                    }
+                    itb[j * kWarp + lane] = my_it;
+                    __syncwarp();
+                    FC_STAT(5);
+                }
+                ++j;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) st_release(done, t + 1);
+        if (++sl == kNT) sl = 0;
+    }
+#ifdef MODFX_FC_STATS
+    if (lane == 0 && a.stats) {
+        long long* o = a.stats + (long long)blockIdx.x * 12;
+        for (int k = 0; k < 6; ++k) { o[k] = st_cnt[k]; o[6 + k] = st_cyc[k]; }
+    }
+#endif
+}
+
 // apply_tremolo, fx.py:13-22: ((1 - mix) * x) + ((mix * mod) * x); one block per (example, channel).
 template <int MODE>
 __global__ void __launch_bounds__(256) tremolo_kernel(const FcArgs a) {
@@ -715,6 +1247,42 @@ extern "C" int modfx_flanger_chorus_f32(const float* x, float* y, int32_t B, int
             MODFX_CUDA_OK(cudaGetLastError());
         }
     }
+    // The latency-oriented CTA-per-delay-line kernel covers a modulation signal read from memory (audio rate or control
+    // rate) and control rows synthesised in-kernel up to kLoSmemMax points; the one-warp kernel keeps the rest (an
+    // audio-rate LFO synthesised per sample, very long synthesised control rows) and MODFX_FC_KERNEL=warp forces it.
+#ifdef MODFX_FC_STATS
+    {
+        const char* sp = getenv("MODFX_FC_STATS_PTR");
+        a.stats = sp ? reinterpret_cast<long long*>(strtoull(sp, nullptr, 0)) : nullptr;
+    }
+#endif
+    const char* force = getenv("MODFX_FC_KERNEL");
+    const bool force_warp = force && force[0] == 'w';
+    const bool cta_ok = !force_warp && (mode == kAudioRate || (mode == kControlRate && (!a.lfo_freq || a.n_lo <= kLoSmemMax)));
+    if (cta_ok) {
+        const int lo_smem = (mode == kControlRate && a.lfo_freq) ? ((a.n_lo + 3) & ~3) : 0;
+        const size_t csmem = sizeof(float) * (16 + (size_t)kNT * kSlotFloats +
+                                              (size_t)kCtaProd * kXDepth * kTile * (mode == kAudioRate ? 2 : 1) +
+                                              (size_t)lo_smem + (size_t)ring);
+        if (csmem > 200 * 1024)
+            return fail(MODFX_ERR_UNSUPPORTED, "delay line of %d samples needs %zu B of shared memory", a.M, csmem);
+#define LAUNCH_CTA(MODE)                                                                                  \
+    do {                                                                                                  \
+        if (csmem > 48 * 1024)                                                                            \
+            MODFX_CUDA_OK(cudaFuncSetAttribute(fc_cta_kernel<MODE, SYNTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)); \
+        fc_cta_kernel<MODE, SYNTH><<<grid, kCtaThreads, csmem, s>>>(a, lo_smem);                          \
+    } while (0)
+#define SYNTH false
+        if (mode == kAudioRate) LAUNCH_CTA(kAudioRate);
+        else if (!a.lfo_freq) LAUNCH_CTA(kControlRate);
+#undef SYNTH
+#define SYNTH true
+        else LAUNCH_CTA(kControlRate);
+#undef SYNTH
+#undef LAUNCH_CTA
+        MODFX_CUDA_OK(cudaGetLastError());
+        return MODFX_OK;
+    }
 #define LAUNCH_FC(MODE)                                                                                   \
     do {                                                                                                  \
         if (smem > 48 * 1024)                                                                             \
@@ -728,6 +1296,13 @@ extern "C" int modfx_flanger_chorus_f32(const float* x, float* y, int32_t B, int
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
 }
+
+#ifdef MODFX_FC_STATS
+extern "C" int modfx_fc_serial_stats(unsigned long long* out4) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out4, modfx::g_serial_stats, sizeof(unsigned long long) * 4);
+}
+#endif
 
 extern "C" int modfx_tremolo_f32(const float* x, float* y, int32_t B, int32_t C, int64_t N,
                                  const modfx_mod_source* mod, modfx_param mix, void* stream) {

@@ -46,17 +46,21 @@ class InterwovenRenderer:
         # depends on nothing) on a low-priority one: the hardware fills the gaps of the chains with it
         self._streams = ([torch.cuda.Stream(device=self.device, priority=-1) for _ in range(3)] +
                          [torch.cuda.Stream(device=self.device, priority=0)]) if concurrent else None
-        self._idx_cache: Dict[int, Tuple[Tensor, ...]] = {}
+        self._idx_cache: Dict[Tuple[int, bytes], Tuple[Tensor, ...]] = {}
 
     # ------------------------------------------------------------------ helpers
     def _groups(self, effect: Tensor, lo: int = 0, hi: Optional[int] = None):
-        """Index lists (relative to `lo`) of the flanger / chorus / phaser examples in effect[lo:hi]."""
+        """Index lists (relative to `lo`) of the flanger / chorus / phaser examples in effect[lo:hi].
+        Cached by CONTENT (the bytes of effect[lo:hi]), so a caller that refills one `effect` buffer in place
+        between steps gets fresh lists; values outside {0, 1, 2} are rejected (their rows would stay unwritten)."""
         hi = effect.numel() if hi is None else hi
-        key = (id(effect), lo, hi)
+        e = effect.detach().reshape(-1)[lo:hi].to("cpu", torch.int64).contiguous()
+        key = (hi - lo, e.numpy().tobytes())
         hit = self._idx_cache.get(key)
-        if hit is not None and hit[0] is effect:
-            return hit[1:]
-        e = effect.detach().cpu()[lo:hi]
+        if hit is not None:
+            return hit
+        if e.numel() and (int(e.min()) < FLANGER or int(e.max()) > PHASER):
+            raise ValueError("effect ids must be 0 (flanger), 1 (chorus) or 2 (phaser)")
         groups = []
         for k in (FLANGER, CHORUS, PHASER):
             idx = torch.nonzero(e == k).reshape(-1).to(torch.int32)
@@ -64,8 +68,8 @@ class InterwovenRenderer:
         dry_rows = torch.arange(hi - lo, dtype=torch.int32, device=self.device)
         if len(self._idx_cache) > 64:
             self._idx_cache.clear()
-        self._idx_cache[key] = (effect, *groups, dry_rows)
-        return (*groups, dry_rows)
+        self._idx_cache[key] = (*groups, dry_rows)
+        return self._idx_cache[key]
 
     def alloc_outputs(self, B: int) -> Tuple[Tensor, Tensor]:
         wet = torch.empty((B, 1, self.n_samples), device=self.device, dtype=torch.float32)
