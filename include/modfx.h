@@ -141,6 +141,26 @@ int modfx_stretch_sections_f32(const float* in, float* out, int32_t B, int64_t n
                                const int32_t* out_start, void* stream);
 
 /*
+ * Replaces make_combined_mod_sig, mod_extraction/modulations.py:191-210, for a batch of (freq, phase) pairs as
+ * datasets.py:375-380 calls it per example, WITHOUT a host round trip: the caller passes the next raw 32-bit
+ * outputs of the torch global CPU generator (mt19937; one word per util.choice, util.py:32-42) and the device
+ * replays the reference's draw order -- per example one base shape, then one shape per span between consecutive
+ * bottom corners of the base signal.
+ *   out        (B, n) float32
+ *   freq/phase (B,) as make_mod_signal receives them (NOT halved for the rectified shapes; done here)
+ *   shapes     (n_shapes,) modfx_shape ids of the candidate list
+ *   words      (n_words,) uint32 raw generator outputs, device
+ *   base_out   (B,) int32: index into shapes of the base shape each example drew
+ *   consumed_out (2,) int32 device: [0] words consumed (advance the generator by this many), [1] error flag
+ *              (1: n_words too small, 2: more than 64 bottom corners in a base signal) -- on error `out` is invalid
+ *   workspace  modfx_combined_lfo_workspace_bytes(B, n, n_shapes) bytes
+ */
+int64_t modfx_combined_lfo_workspace_bytes(int32_t B, int64_t n, int32_t n_shapes);
+int modfx_combined_lfo_f32(float* out, int32_t B, int64_t n, float sr, const float* freq, const float* phase,
+                           const int32_t* shapes, int32_t n_shapes, const uint32_t* words, int64_t n_words,
+                           int32_t* base_out, int32_t* consumed_out, void* workspace, void* stream);
+
+/*
  * Post-processing of extracted LFOs (eval path), mod_extraction/modulations.py:259-362.  Rows are
  * independent (n frames each, 345 for 2 s of audio); all float32 arithmetic in the reference's order.
  *   modfx_smoothen_f32         replaces smoothen, modulations.py:358-362: out (rows, n - window + 1) =

@@ -64,6 +64,8 @@ _SIGNATURES = {
     "modfx_find_corners_f32": ([_vp, _vp, _vp, _i64, _i64, _vp], ctypes.c_int),
     "modfx_lfo_sections_f32": ([_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "modfx_stretch_sections_f32": ([_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "modfx_combined_lfo_workspace_bytes": ([_i32, _i64, _i32], _i64),
+    "modfx_combined_lfo_f32": ([_vp, _i32, _i64, ctypes.c_float, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
     "modfx_smoothen_f32": ([_vp, _vp, _i64, _i64, _i32, _vp], ctypes.c_int),
     "modfx_stretch_corners_f32": ([_vp, _vp, _i64, _i64, _i32, _vp], ctypes.c_int),
     "modfx_check_mod_sig_f32": ([_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp], ctypes.c_int),

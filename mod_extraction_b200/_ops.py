@@ -291,6 +291,25 @@ def stretch_sections(x: Tensor, sec_off, in_start, in_len, new_len, out_start) -
     return out
 
 
+def combined_lfo(n: int, sr: float, freq: Tensor, phase: Tensor, shapes: Tensor, words: Tensor):
+    """Batched make_combined_mod_sig with the reference's draw order replayed on the device (modulations.py:191-210).
+    freq / phase (B,) float32 CUDA, shapes (S,) int32 CUDA, words (K,) raw generator outputs as int32 / uint32 CUDA.
+    Returns (out (B, n), base (B,) int32 index into shapes, consumed (2,) int32 = [words used, error flag])."""
+    _require_cuda(freq, "freq")
+    dev = freq.device
+    B, S = freq.numel(), shapes.numel()
+    out = torch.empty((B, n), device=dev, dtype=torch.float32)
+    base = torch.empty((B,), device=dev, dtype=torch.int32)
+    consumed = torch.zeros((2,), device=dev, dtype=torch.int32)
+    L = _lib.lib()
+    ws = torch.empty((max(1, int(L.modfx_combined_lfo_workspace_bytes(B, n, S))),), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.check(L.modfx_combined_lfo_f32(_ptr(out), B, n, float(sr), _ptr(freq), _ptr(phase), _ptr(shapes), S,
+                                            _ptr(words), words.numel(), _ptr(base), _ptr(consumed), _ptr(ws), _stream()))
+    ws.record_stream(torch.cuda.current_stream(dev))
+    return out, base, consumed
+
+
 # ---- LFO-net body (SURVEY 8f N3), channels-last activations -----------------------------------------------
 def cnn_layernorm(x: Tensor, x_is_nchw: bool = False, eps: float = 1e-5, round_tf32: bool = False,
                   out: Optional[Tensor] = None) -> Tensor:

@@ -5,6 +5,8 @@
 // (make_rand_mod_signal, the phaser ground-truth LFO of datasets.py:442-450, targets at 345 frames).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace modfx {
 namespace {
 
@@ -192,6 +194,155 @@ extern "C" int modfx_stretch_sections_f32(const float* in, float* out, int32_t B
     if (gx > 256) gx = 256;
     stretch_sections_kernel<<<dim3(gx, B), 256, 0, as_stream(stream)>>>(in, out, n, sec_off, in_start, in_len,
                                                                        new_len, out_start);
+    MODFX_CUDA_OK(cudaGetLastError());
+    return MODFX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// make_combined_mod_sig for a whole batch without a host round trip (reference modulations.py:191-210, called per
+// example at datasets.py:375-380).  The reference draws, per example, one base shape and then one shape per span
+// between consecutive bottom corners of the base signal -- a data-dependent number of draws from the torch global
+// CPU generator.  The caller hands over the generator's next raw 32-bit words (mod_extraction_b200/_rng.py: one
+// word per util.choice); the device replays the draw order:
+//   1. every candidate base shape of every example is rendered (combined_cand_kernel);
+//   2. the bottom corners of every candidate are listed (corner_list_kernel, one warp per row);
+//   3. ONE thread walks the examples in order: base = shapes[word % S], sections = corners - 1, next example starts
+//      1 + sections words later (combined_scan_kernel) -- integer work only, ~100 cycles per example;
+//   4. every example takes its base candidate and overwrites the spans with make_mod_signal(len, len, 1.0, 0.0, shape)
+//      (combined_fill_kernel; later spans win at shared end points like the reference's in-order slice assignment).
+// The number of words consumed comes back so the host can advance the generator by exactly that much.
+namespace modfx {
+namespace {
+
+constexpr int kMaxCorners = 64;     // bottom corners listed per candidate row (a 2 s control-rate LFO below 30 Hz has fewer)
+
+__global__ void __launch_bounds__(256) combined_cand_kernel(float* __restrict__ cand, int n, float sr,
+                                                            const float* __restrict__ freq, const float* __restrict__ phase,
+                                                            const int32_t* __restrict__ shapes, int S) {
+    const int row = blockIdx.y;                 // b * S + k
+    const int b = row / S, k = row - b * S;
+    const int shape = shapes[k];
+    const bool rect = shape == MODFX_SHAPE_RECT_COS || shape == MODFX_SHAPE_INV_RECT_COS;
+    // modulations.py:26-29: frequency and phase are halved for the rectified shapes (exact in float32)
+    const LfoDesc d = make_lfo_desc(rect ? freq[b] * 0.5f : freq[b], rect ? phase[b] * 0.5f : phase[b], shape, 1.0f, sr);
+    float* o = cand + (int64_t)row * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) o[i] = lfo_value(d, i);
+}
+
+// bottom corners of find_corners (modulations.py:219-238), as an index list per row
+__global__ void __launch_bounds__(128) corner_list_kernel(const float* __restrict__ mod, int rows, int n,
+                                                          int16_t* __restrict__ idx, int32_t* __restrict__ cnt) {
+    const int row = blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* m = mod + (int64_t)row * n;
+    int16_t* out = idx + (int64_t)row * kMaxCorners;
+    int c = 0;
+    for (int i0 = 0; i0 < n; i0 += kWarp) {
+        const int i = i0 + lane;
+        bool fb = false;
+        if (i >= 1 && i <= n - 2) {
+            const float dl = __fsub_rn(m[i], m[i - 1]);
+            const float dr = __fadd_rn(__fsub_rn(m[i + 1], m[i]), 1e-16f);
+            const float neg = (dl < 0.0f) ? dl : 0.0f;
+            fb = (-floorf(__fmul_rn(neg, dr)) == 1.0f);
+        }
+        const unsigned bal = __ballot_sync(kFull, fb);
+        if (fb) {
+            const int pos = c + __popc(bal & ((1u << lane) - 1u));
+            if (pos < kMaxCorners) out[pos] = (int16_t)i;
+        }
+        c += __popc(bal);
+    }
+    if (lane == 0) cnt[row] = c;
+}
+
+__global__ void combined_scan_kernel(const uint32_t* __restrict__ words, int64_t n_words, const int32_t* __restrict__ cnt,
+                                     int B, int S, int32_t* __restrict__ base, int32_t* __restrict__ woff,
+                                     int32_t* __restrict__ consumed) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int64_t off = 0;
+    int err = 0;
+    for (int b = 0; b < B; ++b) {
+        woff[b] = (int32_t)off;
+        if (off >= n_words) { err = 1; base[b] = 0; continue; }
+        const int k = (int)(words[off] % (uint32_t)S);                  // util.choice(shapes), modulations.py:196
+        base[b] = k;
+        const int c = cnt[b * S + k];
+        if (c > kMaxCorners) err = 2;
+        const int nsec = (c > 1) ? c - 1 : 0;                           // modulations.py:203-204
+        off += 1 + nsec;
+    }
+    if (off > n_words) err = 1;
+    woff[B] = (int32_t)off;
+    consumed[0] = (int32_t)off;
+    consumed[1] = err;
+}
+
+__global__ void __launch_bounds__(256) combined_fill_kernel(float* __restrict__ out, int n, const float* __restrict__ cand,
+                                                            const int16_t* __restrict__ idx, const int32_t* __restrict__ cnt,
+                                                            const int32_t* __restrict__ base, const int32_t* __restrict__ woff,
+                                                            const uint32_t* __restrict__ words,
+                                                            const int32_t* __restrict__ shapes, int S) {
+    __shared__ int16_t cs[kMaxCorners];
+    const int b = blockIdx.y;
+    const int row = b * S + base[b];
+    const int c = min(cnt[row], kMaxCorners);
+    for (int i = threadIdx.x; i < c; i += blockDim.x) cs[i] = idx[(int64_t)row * kMaxCorners + i];
+    __syncthreads();
+    const float* src = cand + (int64_t)row * n;
+    float* o = out + (int64_t)b * n;
+    const int64_t w0 = woff[b] + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float v = src[i];
+        if (c > 1 && i >= cs[0] && i <= cs[c - 1]) {
+            // span s covers [corner s, corner s + 1]; spans are assigned in order, so a shared end point keeps the later one
+            int s = 0;
+            for (int j = 1; j <= c - 2; ++j)
+                if (cs[j] <= i) s = j;
+            const int start = cs[s];
+            const float len = (float)(cs[s + 1] - start + 1);
+            const int shape = shapes[words[w0 + s] % (uint32_t)S];      // util.choice(shapes), modulations.py:207
+            const bool rect = shape == MODFX_SHAPE_RECT_COS || shape == MODFX_SHAPE_INV_RECT_COS;
+            const LfoDesc d = make_lfo_desc(rect ? 0.5f : 1.0f, 0.0f, shape, 1.0f, len);       // modulations.py:208
+            v = lfo_value(d, i - start);
+        }
+        o[i] = v;
+    }
+}
+
+int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+
+}  // namespace
+}  // namespace modfx
+
+extern "C" int64_t modfx_combined_lfo_workspace_bytes(int32_t B, int64_t n, int32_t n_shapes) {
+    if (B <= 0 || n <= 0 || n_shapes <= 0) return 0;
+    const int64_t rows = (int64_t)B * n_shapes;
+    return align256(rows * n * 4) + align256(rows * kMaxCorners * 2) + align256(rows * 4) + align256(((int64_t)B + 1) * 4);
+}
+
+extern "C" int modfx_combined_lfo_f32(float* out, int32_t B, int64_t n, float sr, const float* freq, const float* phase,
+                                      const int32_t* shapes, int32_t n_shapes, const uint32_t* words, int64_t n_words,
+                                      int32_t* base_out, int32_t* consumed_out, void* workspace, void* stream) {
+    MODFX_REQUIRE(out && freq && phase && shapes && words && base_out && consumed_out && workspace, "NULL pointer");
+    MODFX_REQUIRE(B >= 0 && n >= 3 && n <= 32767 && sr > 0.0f, "bad arguments B=%d n=%lld sr=%g", B, (long long)n, sr);
+    MODFX_REQUIRE(n_shapes >= 1 && n_shapes <= 64 && n_words >= 0, "bad shape list / word count");
+    if (B == 0) return MODFX_OK;
+    const int64_t rows = (int64_t)B * n_shapes;
+    MODFX_REQUIRE(rows <= 65535 * 64ll, "too many candidate rows");
+    char* w = static_cast<char*>(workspace);
+    float* cand = reinterpret_cast<float*>(w);          w += align256(rows * n * 4);
+    int16_t* idx = reinterpret_cast<int16_t*>(w);       w += align256(rows * kMaxCorners * 2);
+    int32_t* cnt = reinterpret_cast<int32_t*>(w);       w += align256(rows * 4);
+    int32_t* woff = reinterpret_cast<int32_t*>(w);
+    cudaStream_t s = as_stream(stream);
+    const int gx = (int)std::min<int64_t>((n + 255) / 256, 64);
+    MODFX_REQUIRE(rows <= 65535, "B * n_shapes = %lld exceeds grid.y", (long long)rows);
+    combined_cand_kernel<<<dim3(gx, (unsigned)rows), 256, 0, s>>>(cand, (int)n, sr, freq, phase, shapes, n_shapes);
+    corner_list_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(cand, (int)rows, (int)n, idx, cnt);
+    combined_scan_kernel<<<1, 32, 0, s>>>(words, n_words, cnt, B, n_shapes, base_out, woff, consumed_out);
+    combined_fill_kernel<<<dim3(gx, (unsigned)B), 256, 0, s>>>(out, (int)n, cand, idx, cnt, base_out, woff, words, shapes, n_shapes);
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
 }

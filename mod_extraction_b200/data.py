@@ -35,33 +35,50 @@ FLANGER_PARAM_ORDER = ("feedback", "min_delay_width", "width", "depth", "mix")  
 # --------------------------------------------------------------------------------------------- N1
 
 def sample_mod_sig_batch(mod_cfg: Dict[str, Any], batch_size: int, n_samples: int, sr: float,
-                         device=None) -> Tuple[T, Dict[str, Any]]:
+                         device=None, exact_stream: bool = True) -> Tuple[T, Dict[str, Any]]:
     """Batched LFO part of RandomAudioChunkAndModSigDataset.__getitem__ (datasets.py:367-397).
 
-    Draw order per example, as in the reference: rate (scipy log-uniform), phase (torch uniform), shape
-    (torch randint); for "combined" configs the per-section shape draws follow inside
-    ``make_combined_mod_sig_batch`` example by example, for "quasiperiodic" the stretch draws inside
-    ``make_quasi_periodic_batch``.  Note: in the reference the draws of one example (including the
-    combined / quasi-periodic ones) are contiguous in the stream; here all (rate, phase, shape) triples
-    are drawn first and the section draws follow, so batched results equal the reference's only for
-    plain LFOs unless ``batch_size == 1``.
+    Draw order per example, as in the reference: rate (scipy log-uniform on numpy's global RNG), phase (torch
+    uniform), shape (torch randint), then -- BEFORE the next example's triple -- the draws of
+    ``make_combined_mod_sig`` ("combined" configs: base shape + one shape per span) and of ``make_quasi_periodic``
+    ("quasiperiodic" configs: two draws per section).  How many draws an example makes depends on the corners of
+    its own signal, and its phase comes from the same stream, so for those configs the stream can only be followed
+    example by example: ``exact_stream=True`` (default) does that (one small launch sequence per example, like the
+    reference's per-item ``__getitem__``), and under a given seed reproduces the reference's LFOs and ``fx_params``.
+    ``exact_stream=False`` draws all (rate, phase, shape) triples first and lets the batched generators make the
+    section draws afterwards: one launch sequence per batch, same distribution, different stream for B > 1.
+    Plain LFO configs need no such choice: the batched form IS the reference's stream.
     Returns (mod_sig (B, n_samples // 100) on the GPU, fx_params with rate_hz, phase, shape, exp).
     """
     n_lo, sr_lo = n_samples // 100, sr // 100                                   # datasets.py:377-382
-    rates, phases, shapes = [], [], []
+    exp = mod_cfg["exp"]
+    combined, quasi = bool(mod_cfg.get("combined")), bool(mod_cfg.get("quasiperiodic"))
+    q_args = [mod_cfg.get(k, 0.2) for k in ("l_min", "l_max", "r_min", "r_max")] + [mod_cfg.get("lr_split", 0.5)]
+    rates, phases, shapes, rows = [], [], [], []
+    per_example = exact_stream and (combined or quasi) and batch_size > 1
     for _ in range(batch_size):
         rates.append(util.sample_log_uniform(mod_cfg["rate_hz"]["min"], mod_cfg["rate_hz"]["max"]))
         phases.append(util.sample_uniform(mod_cfg["phase"]["min"], mod_cfg["phase"]["max"]))
         shapes.append(util.choice(mod_cfg["shapes"]))
-    exp = mod_cfg["exp"]
-    if mod_cfg.get("combined"):
-        mod_sig = make_combined_mod_sig_batch(n_lo, sr_lo, rates, phases, mod_cfg["shapes"], device)
+        if per_example:                                                         # datasets.py:375-390, one item
+            if combined:
+                row = make_combined_mod_sig_batch(n_lo, sr_lo, rates[-1:], phases[-1:], mod_cfg["shapes"], device)
+            else:
+                row = make_mod_signal_batch(n_lo, sr_lo, rates[-1:], phases[-1:], shapes[-1:],
+                                            None if exp == 1.0 else [exp], device)
+            if quasi:
+                row = make_quasi_periodic_batch(row, *q_args)
+            rows.append(row)
+    if per_example:
+        mod_sig = tr.cat(rows, 0)
     else:
-        mod_sig = make_mod_signal_batch(n_lo, sr_lo, rates, phases, shapes, None if exp == 1.0 else [exp] * batch_size,
-                                        device)
-    if mod_cfg.get("quasiperiodic"):
-        mod_sig = make_quasi_periodic_batch(mod_sig, mod_cfg["l_min"], mod_cfg["l_max"], mod_cfg["r_min"],
-                                            mod_cfg["r_max"], mod_cfg["lr_split"])
+        if combined:
+            mod_sig = make_combined_mod_sig_batch(n_lo, sr_lo, rates, phases, mod_cfg["shapes"], device)
+        else:
+            mod_sig = make_mod_signal_batch(n_lo, sr_lo, rates, phases, shapes,
+                                            None if exp == 1.0 else [exp] * batch_size, device)
+        if quasi:
+            mod_sig = make_quasi_periodic_batch(mod_sig, *q_args)
     fx_params = {"rate_hz": tr.tensor(rates, dtype=tr.float64), "phase": tr.tensor(phases, dtype=tr.float64),
                  "shape": shapes, "exp": tr.full((batch_size,), float(exp), dtype=tr.float64)}     # default_collate layout
     return mod_sig, fx_params
@@ -77,10 +94,12 @@ class FlangerRenderStep:
     """GPU equivalent of ``FlangerCPUDataModule`` 's ``setup`` + ``on_before_batch_transfer``
     (data_modules.py:379-385, 419-458): ``(dry, mod_sig, fx_params)`` in, ``(dry, wet, mod_sig, fx_params)`` out
     with the same fx_params keys.  The x100 upsample of data_modules.py:454-455 is fused into the effect
-    kernel, so the returned ``mod_sig`` stays at control rate unless ``return_audio_rate_mod=True``."""
+    kernel; the returned ``mod_sig`` is nevertheless the audio-rate one, as in the reference (data_modules.py:454-458),
+    unless ``return_audio_rate_mod=False`` (a consumer that resamples it to 345 frames anyway, lightning.py:114, can
+    skip the (B, n_samples) tensor)."""
 
     def __init__(self, fx_config: Dict[str, Any], batch_size: int, n_samples: int, sr: float,
-                 return_audio_rate_mod: bool = False) -> None:
+                 return_audio_rate_mod: bool = True) -> None:
         self.fx_config = fx_config
         self.batch_size = batch_size
         fl = fx_config["flanger"]

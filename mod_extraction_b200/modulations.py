@@ -194,15 +194,42 @@ def make_quasi_periodic(mod_sig: T,
     return out.cpu() if on_cpu else out
 
 
-def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes: List[str], device=None) -> T:
-    """make_combined_mod_sig for B (freq, phase) pairs.  The number of RNG draws of an example
-    depends on the corners of the base shape it drew, so every candidate base shape is rendered and
-    corner-searched on the GPU first; the host then replays the reference's draw order exactly."""
+def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes: List[str], device=None,
+                                return_base: bool = False, host_replay: bool = False):
+    """make_combined_mod_sig for B (freq, phase) pairs, equivalent to calling the reference function on pair 0, then
+    pair 1, ... under the same state of the torch global CPU generator, which it leaves where that loop would.
+
+    The number of draws of an example depends on the corners of the base shape it drew.  The generator's next raw
+    words are produced in one go (``_rng.TorchMT``), every candidate base shape is rendered and corner-searched on
+    the GPU, one device thread replays the reference's draw order, and the generator is advanced by the number of
+    words that replay consumed: one launch sequence and one 8-byte read-back for the whole batch instead of a python
+    loop of scalar ``torch.randint`` calls (0.2 s for 4096 examples).  ``host_replay=True`` keeps that loop (the
+    cross-check of the device replay, and the fallback for signals with more than 64 bottom corners)."""
     device = _device() if device is None else device
     f = tr.as_tensor(freqs, dtype=tr.float64).reshape(-1)
     p = tr.as_tensor(phases, dtype=tr.float64).reshape(-1)
     B, S = f.numel(), len(shapes)
+    assert B == p.numel() and S > 0
+    assert bool((f > 0.0).all()) and bool((f < sr / 2.0).all())             # modulations.py:23
+    assert bool((p >= -2 * tr.pi).all()) and bool((p <= 2 * tr.pi).all())   # modulations.py:24
     sid = shape_ids(shapes)
+    if not host_replay and B > 0 and 3 <= n_samples <= 32767:
+        from ._rng import TorchMT
+        mt = TorchMT()
+        per_example = 1 + 16                # base draw + sections; a 2 s control-rate LFO below 3 Hz has at most 7
+        for _ in range(2):
+            words = tr.from_numpy(mt.words(B * per_example).view("int32"))
+            out, base, consumed = _ops.combined_lfo(n_samples, sr, f.float().to(device, non_blocking=True),
+                                                    p.float().to(device, non_blocking=True), sid.to(device),
+                                                    words.to(device, non_blocking=True))
+            used, err = consumed.tolist()
+            if err == 0:
+                mt.consume(used)
+                return (out, base) if return_base else out
+            if err != 1:
+                break
+            mt = TorchMT()                  # ran out of words: hand over more and replay
+            per_example *= 8
     cand = make_mod_signal_batch(n_samples, sr, f.repeat_interleave(S), p.repeat_interleave(S), sid.repeat(B),
                                  None, device)                                   # (B*S, n)
     _, bottom = _ops.find_corners(cand)
@@ -224,6 +251,8 @@ def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes
     out = cand[tr.tensor(base, device=device)].contiguous()
     if sec_start:
         _ops.lfo_sections_(out, sec_off, sec_start, sec_len, sec_shape)
+    if return_base:
+        return out, (tr.tensor(base, dtype=tr.int32) % S).to(device)
     return out
 
 

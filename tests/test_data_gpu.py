@@ -87,3 +87,50 @@ def test_cache_roundtrip_and_naming(tmp_path):
         assert f["shape"] == fx["shape"][j] and f["exp"] == 1.0
         seen += 1
     assert seen == B
+
+
+class _LiveDraws:
+    """The reference's util.sample_uniform / util.choice on the torch global CPU generator (util.py:32-49)."""
+
+    def uniform(self, low, high):
+        return ((torch.rand(1) * (high - low)) + low).item()
+
+    def choice(self, n):
+        return torch.randint(low=0, high=n, size=(1,)).item()
+
+
+@pytest.mark.parametrize("kind", ["combined", "quasiperiodic"])
+def test_sample_mod_sig_follows_the_reference_stream_example_by_example(kind):
+    """datasets.py:365-398 for the eval_lfo_combined / eval_lfo_quasi configurations: every example's triple AND its
+    section draws are contiguous in the torch stream.  The restatement below walks the stream like __getitem__ does."""
+    from mod_extraction_b200.data import sample_mod_sig_batch
+    from scipy.stats import loguniform
+    cfg = dict(MOD_CFG)
+    cfg["rate_hz"] = {"min": 1.0, "max": 3.0} if kind == "combined" else {"min": 0.5, "max": 2.0}
+    q = dict(l_min=0.10, l_max=0.3333, r_min=0.10, r_max=0.3333, lr_split=0.5)      # configs/eval_lfo_quasi.yml:49-54
+    cfg[kind] = True
+    cfg.update(q)
+    B, N = 12, 88200
+    torch.manual_seed(21)
+    np.random.seed(21)
+    mod, fxp = sample_mod_sig_batch(cfg, B, N, SR)
+    tail = torch.rand(3)
+    torch.manual_seed(21)
+    np.random.seed(21)
+    draws = _LiveDraws()
+    for b in range(B):
+        rate = float(loguniform.rvs(cfg["rate_hz"]["min"], cfg["rate_hz"]["max"], size=1)[0])
+        phase = draws.uniform(0.0, 6.28318530718)
+        shape = SHAPES6[draws.choice(6)]
+        assert fxp["rate_hz"][b].item() == rate and fxp["phase"][b].item() == phase and fxp["shape"][b] == shape, b
+        if kind == "combined":
+            ref = oracle.make_combined_mod_sig(882, 441, rate, phase, SHAPES6, rng=draws)
+        else:
+            ref = oracle.make_quasi_periodic(oracle.make_mod_signal(882, 441, rate, phase, shape), rng=draws, **q)
+        assert np.abs(mod[b].cpu().numpy() - ref).max() <= 1e-6, b
+    assert torch.equal(tail, torch.rand(3)), "generator state after the batch"
+    # the one-launch form draws the same triples only for batch 1 (documented)
+    torch.manual_seed(21)
+    np.random.seed(21)
+    mod1, _ = sample_mod_sig_batch(cfg, 1, N, SR, exact_stream=False)
+    assert torch.equal(mod1[0], mod[0])

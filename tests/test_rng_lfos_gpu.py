@@ -72,3 +72,24 @@ def test_combined_batch_equals_sequential_calls():
     bat = make_combined_mod_sig_batch(882, 441, f, ph, SHAPES6)
     assert torch.equal(seq, bat)
     assert float(bat.min()) >= 0.0 and float(bat.max()) <= 1.0
+
+
+@pytest.mark.parametrize("B,seed", [(1, 3), (64, 5), (4096, 43)])
+def test_combined_device_replay_equals_host_replay(B, seed):
+    """The device replay of make_combined_mod_sig's draw order (raw generator words handed to the GPU) gives the signals,
+    the base shapes and the final generator state of the per-example python loop of scalar torch.randint calls."""
+    from mod_extraction_b200.modulations import make_combined_mod_sig_batch
+    rng = np.random.RandomState(seed)
+    f = np.exp(rng.uniform(np.log(1.0), np.log(3.0), B))
+    ph = rng.uniform(0, 2 * np.pi, B)
+    torch.manual_seed(seed)
+    torch.rand(seed * 37)                                       # start somewhere inside a generator block
+    slow, base_slow = make_combined_mod_sig_batch(882, 441, f, ph, SHAPES6, return_base=True, host_replay=True)
+    next_slow = torch.rand(5)
+    torch.manual_seed(seed)
+    torch.rand(seed * 37)
+    fast, base_fast = make_combined_mod_sig_batch(882, 441, f, ph, SHAPES6, return_base=True)
+    next_fast = torch.rand(5)
+    assert torch.equal(base_slow.cpu(), base_fast.cpu())
+    assert torch.equal(slow, fast)
+    assert torch.equal(next_slow, next_fast), "the generator must end where the reference's loop leaves it"
