@@ -80,12 +80,15 @@ class InterwovenRenderer:
     @torch.no_grad()
     def render_host(self, dry_h: Tensor, effect: Tensor, mod_lo_h: Tensor, fc_h: Dict[str, Tensor],
                     ph_h: Dict[str, Tensor], wet_h: Tensor, logmel: Tensor, stat_h: Optional[Tensor] = None,
-                    chunk: int = 512, dry_d: Optional[Tensor] = None, wet_d: Optional[Tensor] = None) -> None:
+                    chunk: int = 512, dry_d: Optional[Tensor] = None, wet_d: Optional[Tensor] = None,
+                    logmel_h: Optional[Tensor] = None) -> None:
         """Host-buffer entry point: pinned host dry audio + parameters in, wet audio out to the pinned host
         tensor `wet_h`; the log-mel tensor stays on the GPU (`logmel`, (B,2,n_mels,n_frames)) where the
-        extractor consumes it, and `stat_h` (B, 2) receives its per-example mean.  The batch is cut into
-        chunks so that the H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1
-        overlap (PCIe is full duplex); the call returns when everything has landed."""
+        extractor consumes it, and `stat_h` (B, 2) receives its per-example mean; with `logmel_h` (pinned, same
+        shape) the log-mel tensor is delivered to the host as well.  `mod_lo_h` may already live on the device
+        (LFOs generated there).  The batch is cut into chunks so that the H2D copy of chunk i+1, the kernels of
+        chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex); the call returns when everything has
+        landed."""
         B, _, N = dry_h.shape
         if dry_d is None:
             dry_d = torch.empty((B, 1, N), device=self.device, dtype=torch.float32)
@@ -96,7 +99,7 @@ class InterwovenRenderer:
         s_in, s_run, s_out = self._io_streams
         cur = torch.cuda.current_stream(self.device)
         start = torch.cuda.Event()
-        start.record(cur)
+        start.record(cur)                                   # e.g. LFOs generated on `cur` just before this call
         for st in self._io_streams:
             st.wait_event(start)
         fc_keys = ("feedback", "min_delay_width", "width", "depth", "mix")
@@ -117,7 +120,7 @@ class InterwovenRenderer:
         for lo, hi in edges:
             with torch.cuda.stream(s_in):
                 dry_d[lo:hi].copy_(dry_h[lo:hi], non_blocking=True)
-                m = mod_lo_h[lo:hi].to(self.device, non_blocking=True)
+                m = mod_lo_h[lo:hi] if mod_lo_h.is_cuda else mod_lo_h[lo:hi].to(self.device, non_blocking=True)
                 f = {k: fc_h[k][lo:hi].to(self.device, non_blocking=True) for k in fc_keys}
                 p = {k: ph_h[k][lo:hi].to(self.device, non_blocking=True) for k in ph_keys}
                 ev_in = torch.cuda.Event()
@@ -133,6 +136,8 @@ class InterwovenRenderer:
             s_out.wait_event(ev_run)
             with torch.cuda.stream(s_out):
                 wet_h[lo:hi].copy_(wet_d[lo:hi], non_blocking=True)
+                if logmel_h is not None:
+                    logmel_h[lo:hi].copy_(logmel[lo:hi], non_blocking=True)
                 if stat_h is not None:
                     stat_h[lo:hi].copy_(st_d, non_blocking=True)
                     st_d.record_stream(s_out)
