@@ -146,17 +146,18 @@ def _blas_single_threaded():
         return contextlib.nullcontext()
 
 
-def _oracle_logmel_rows(both, threads):
+def _oracle_logmel_rows(both, threads, fb=None):
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle
-    fb = oracle.mel_filterbank()
+    fb = oracle.mel_filterbank() if fb is None else fb
     with _blas_single_threaded(), ThreadPoolExecutor(max_workers=threads) as ex:
         rows = list(ex.map(lambda b: oracle.log_mel(both[b], fb=fb), range(both.shape[0])))
     return np.stack(rows)
 
 
-def oracle_step(dry, effect, mod_lo, fc, ph, threads):
-    """Config 4 through the CPU restatement (oracle/): returns (wet, logmel)."""
+def oracle_step(dry, effect, mod_lo, fc, ph, threads, fb=None):
+    """Config 4 through the CPU restatement (oracle/): returns (wet, logmel).  `fb`: mel table to use (parity checks
+    pass the product's, which is torchaudio's own: a from-scratch float32 table differs by ~3e-5 in a few weights)."""
     from oracle import oracle
     n = dry.shape[-1]
     wet = np.empty_like(dry)
@@ -170,7 +171,7 @@ def oracle_step(dry, effect, mod_lo, fc, ph, threads):
     if idx.size:
         wet[idx, 0] = oracle.phaser(dry[idx, 0], float(SR), *[ph[kk][idx] for kk in PH_KEYS])
     both = np.concatenate([dry, wet], axis=1)                    # lightning.py:106
-    return wet, _oracle_logmel_rows(both, threads)
+    return wet, _oracle_logmel_rows(both, threads, fb)
 
 
 def oracle_inputs(B, seed, n=N):

@@ -299,6 +299,27 @@ def lfo_estimates(B, n, seed, noise):
     return tr.clip(x, 0.0, 1.0).float()
 
 
+def gen_logmel_c4():
+    """Config-4-shaped rows (2 channels x 88200 samples -> (2, 256, 345)) of both audio families through the reference's
+    own front end (models.py:170-175,199,207-208)."""
+    print("M1 log-mel front end, config-4-shaped rows")
+    net = rmodels.Spectral2DCNN(in_ch=2, n_samples=88200, sr=SR)
+    net.eval()
+    d = {}
+    cases = [("white_2ch_88200", white((1, 2, 88200), 141)),
+             ("guitar_2ch_88200", tr.cat([guitar(1, 88200, 142), guitar(1, 88200, 143) * 0.5], dim=1))]
+    for i, (name, x) in enumerate(cases):
+        with tr.no_grad():
+            ref = tr.log(tr.clip(net.spectrogram(x), min=net.eps)).numpy()
+        got64 = oracle.log_mel(x.numpy(), fft_dtype=np.float64, fb=net.spectrogram.mel_scale.fb.numpy())
+        report(f"{name} (reference vs float64 FFT)", ref, got64)
+        d[f"x{i}"] = x.numpy()
+        d[f"y{i}"] = ref
+        d[f"name{i}"] = np.array(name)
+    d["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "logmel_c4.npz"), **d)
+
+
 def gen_postproc():
     print("N4 smoothen / stretch_corners / find_valid_mod_sig_indices")
     d = {}
@@ -395,9 +416,9 @@ def gen_cnn():
 if __name__ == "__main__":
     tr.manual_seed(0)
     oracle.build()
-    which = sys.argv[1:] or ["lfo", "interp", "tremolo", "rng", "logmel", "fc", "postproc", "cnn"]
+    which = sys.argv[1:] or ["lfo", "interp", "tremolo", "rng", "logmel", "logmel_c4", "fc", "postproc", "cnn"]
     fns = {"lfo": gen_lfo, "interp": gen_interp, "fc": gen_fc, "tremolo": gen_tremolo, "rng": gen_rng_lfos,
-           "logmel": gen_logmel, "postproc": gen_postproc, "cnn": gen_cnn}
+           "logmel": gen_logmel, "logmel_c4": gen_logmel_c4, "postproc": gen_postproc, "cnn": gen_cnn}
     for w in which:
         fns[w]()
     for f in sorted(os.listdir(HERE)):

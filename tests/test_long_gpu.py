@@ -61,4 +61,4 @@ def test_logmel_60s_shape_and_sampled_frames():
     off = (512 + 2048) // 256                             # frame t of the clip is frame t - t0 + off of the excerpt
     got = y[:, :, :, t0:t0 + nt].cpu().numpy()
     err = np.abs(got - ref[:, :, :, off:off + nt])
-    assert (err <= 1e-4).mean() >= 0.998 and err.max() <= 2e-3
+    assert (err <= 1e-4).mean() >= 0.9999 and err.max() <= 2e-3        # white noise, vs float64 FFT; see test_logmel_gpu

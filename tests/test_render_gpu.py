@@ -25,11 +25,38 @@ def test_renderer_concurrent_equals_serial_and_oracle():
     wb, lb = InterwovenRenderer(bench.N, float(bench.SR), dev, concurrent=False).render(*args)
     torch.cuda.synchronize()
     assert torch.equal(wa, wb) and torch.equal(la, lb)
-    ref_wet, ref_lm = bench.oracle_step(dry, effect, mod_lo, fc, ph, threads=4)
+    from mod_extraction_b200.models import LogMelSpectrogram
+    ref_wet, ref_lm = bench.oracle_step(dry, effect, mod_lo, fc, ph, threads=4, fb=LogMelSpectrogram().fb.numpy())
     fcx = np.nonzero(effect != 2)[0]
     assert np.array_equal(wa.cpu().numpy()[fcx], ref_wet[fcx])
-    err = np.abs(la.cpu().numpy() - ref_lm)
-    assert (err <= 1e-4).mean() >= 0.995
+    # log-mel of rows whose wet audio is bit-identical on both sides (dry halves, flanger / chorus rows): white noise,
+    # float32 FFTs on both sides, each <= ~2e-4 from exact arithmetic
+    err = np.abs(la.cpu().numpy() - ref_lm)[fcx]
+    assert err.max() <= 5e-4 and (err <= 1e-4).mean() >= 0.9999, float(err.max())
+    # effect ids outside {0, 1, 2} are rejected instead of leaving rows unwritten
+    bad = torch.from_numpy(effect.copy())
+    bad[3] = 7
+    with pytest.raises(ValueError):
+        InterwovenRenderer(bench.N, float(bench.SR), dev).render(args[0], bad, *args[2:])
+
+
+def test_renderer_index_lists_follow_in_place_refills():
+    """One `effect` buffer refilled in place between steps (the pinned-buffer pattern) must not get stale index lists."""
+    from mod_extraction_b200.render import InterwovenRenderer
+    dev = torch.device("cuda", 0)
+    B = 6
+    dry, effect, mod_lo, fc, ph = bench.oracle_inputs(B, seed=3)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    R = InterwovenRenderer(bench.N, float(bench.SR), dev)
+    eff = torch.from_numpy(effect.copy())
+    rest = (to(mod_lo), {k: to(v) for k, v in fc.items()}, {k: to(v) for k, v in ph.items()})
+    w1, _ = R.render(to(dry), eff, *rest)
+    w1 = w1.clone()
+    eff.copy_(torch.tensor([1, 1, 0, 0, 2, 2]))                 # same tensor object, new contents
+    w2, _ = R.render(to(dry), eff, *rest)
+    fresh, _ = InterwovenRenderer(bench.N, float(bench.SR), dev).render(to(dry), eff.clone(), *rest)
+    torch.cuda.synchronize()
+    assert torch.equal(w2, fresh) and not torch.equal(w1, w2)
 
 
 def test_render_host_pipelined_equals_device_render():
