@@ -1,6 +1,12 @@
-"""Builds libmodfx.so in-tree with nvcc for sm_100a (no JIT cache, no torch headers)."""
+"""Builds libmodfx.so in-tree with nvcc for sm_100a (no JIT cache, no torch headers).
+
+The library is git-ignored and travels to the GPU box prebuilt, so "is it current?" is decided by CONTENT: the
+sha256 of every file under csrc/, include/modfx.h and the nvcc flags is written beside the library
+(lib/libmodfx.sha256) and compared on every build() -- a library built from other sources is rebuilt (or, where
+nvcc is missing, refused) whatever the file times say."""
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -12,6 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmodfx.so")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
+STAMP_PATH = os.path.join(LIB_DIR, "libmodfx.sha256")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,6 +40,25 @@ def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def source_hash() -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(f for f in NVCC_FLAGS if not os.path.isabs(f)).encode())
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(ROOT, "include", "modfx.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    """The library exists and was built from exactly the sources in the tree."""
+    try:
+        return os.path.exists(LIB_PATH) and open(STAMP_PATH).read().strip() == source_hash()
+    except OSError:
+        return False
+
+
 def _stale(target: str, deps) -> bool:
     if not os.path.exists(target):
         return True
@@ -42,6 +68,8 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
+    if not force and is_current():
+        return LIB_PATH
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "modfx.h"))
@@ -53,6 +81,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
         if force or _stale(o, [s] + headers):
             jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+    if not jobs and os.path.exists(LIB_PATH):
+        # the content hash says the library is not from these sources, the file times say nothing changed: trust the
+        # hash (a prebuilt library that travelled with another tree) and rebuild everything
+        return build(force=True, verbose=verbose)
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -67,6 +99,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(log)
     if jobs or force or _stale(LIB_PATH, objs):
         run([nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    with open(STAMP_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB_PATH
 
 

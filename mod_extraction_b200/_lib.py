@@ -95,6 +95,14 @@ def exported_symbols():
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
+        if LIB_PATH == _DEFAULT_LIB_PATH and os.path.exists(LIB_PATH):
+            from . import _build
+            if not _build.is_current():     # built from other sources than the ones in this tree: never load it silently
+                try:
+                    _build.build()
+                except Exception as exc:
+                    raise RuntimeError(f"{LIB_PATH} was not built from the sources in this tree (content hash mismatch) "
+                                       f"and could not be rebuilt: {exc}") from exc
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m mod_extraction_b200._build` "

@@ -263,7 +263,33 @@ def check_mod_sig(x: Tensor, min_top: int, max_top: int, min_bottom: int, max_bo
 
 
 def _i32(values, device) -> Tensor:
+    if isinstance(values, Tensor):
+        return values.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
     return torch.tensor(values, dtype=torch.int32).to(device, non_blocking=True)
+
+
+def logmel(x: Tensor, window: Tensor, fb_start: Tensor, fb_count: Tensor, fb_weight: Tensor, fb_taps: int, hop: int = 256,
+           eps: float = 1e-7, apply_log: bool = True) -> Tensor:
+    """(..., T) CUDA float32 -> (..., n_mels, T // hop + 1): MelSpectrogram [-> clip -> log] of models.py:170-175,199,207-208
+    with the banded mel table of models.banded() (n_fft = len(window) = 1024)."""
+    _require_cuda(x, "x")
+    x = x.detach().float().contiguous()
+    T, lead = x.size(-1), x.shape[:-1]
+    R = x.numel() // T
+    n_mels, nf = fb_start.numel(), T // hop + 1
+    out = torch.empty(lead + (n_mels, nf), device=x.device, dtype=torch.float32)
+    if R == 0:
+        return out
+    keep = _Keep()
+    w = keep(window.to(device=x.device, dtype=torch.float32).contiguous())
+    s = keep(fb_start.to(device=x.device, dtype=torch.int32).contiguous())
+    c = keep(fb_count.to(device=x.device, dtype=torch.int32).contiguous())
+    fw = keep(fb_weight.to(device=x.device, dtype=torch.float32).contiguous())
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().modfx_logmel_f32(_ptr(x), _ptr(out), R, T, w.numel(), hop, n_mels, _ptr(w), _ptr(s), _ptr(c),
+                                               _ptr(fw), fw.size(1), int(fb_taps), float(eps), 1 if apply_log else 0, 0, 0,
+                                               ctypes.c_void_p(0), 0, _stream()))
+    return out
 
 
 def lfo_sections_(out: Tensor, sec_off, sec_start, sec_len, sec_shape) -> Tensor:

@@ -73,6 +73,11 @@ def test_torch_ops_registered_cuda_only():
     import mod_extraction_b200._torch_ops  # noqa: F401
     assert hasattr(torch.ops.modfx, "flanger_chorus") and hasattr(torch.ops.modfx, "phaser")
     assert hasattr(torch.ops.modfx, "cnn_conv_pool_prelu") and hasattr(torch.ops.modfx, "cnn_head")
+    for name in ("tremolo", "mel_power", "logmel", "find_corners", "lfo_sections", "stretch_sections", "combined_lfo",
+                 "smoothen", "stretch_corners", "check_mod_sig", "lfo", "interp_linear"):      # every op of the path
+        assert hasattr(torch.ops.modfx, name), name
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.modfx.smoothen(torch.zeros(2, 40), 4)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.modfx.cnn_layernorm(torch.zeros(1, 2, 4, 4), True, 1e-5, False)
     with pytest.raises((NotImplementedError, RuntimeError)):
@@ -102,3 +107,20 @@ def test_cnn_entry_points_validate_before_touching_the_gpu():
     assert L.modfx_cnn_head_f32(p, p, nul, 1, 1, 1, 1, 1, p, p, nul) == -1
     assert L.modfx_specaugment_fill_f32(p, 1, 4, 4, 3, 2, 0, 0, 1e-7, 1, nul) == -1                            # f0 > f1
     assert L.modfx_specaugment_fill_f32(p, 1, 4, 4, 0, 0, 0, 0, 1e-7, 1, nul) == 0                             # nothing to mask
+
+
+def test_build_is_keyed_by_source_content():
+    """_build.build() must not reuse a library built from other sources: the hash of csrc/ + include/ + flags is stored
+    beside the library and compared, whatever the file times say."""
+    from mod_extraction_b200 import _build
+    path = _build.build()
+    assert os.path.exists(path)
+    stamp = open(_build.STAMP_PATH).read().strip()
+    assert stamp == _build.source_hash()
+    assert _build.is_current()
+    # a library with a foreign stamp is stale
+    try:
+        open(_build.STAMP_PATH, "w").write("0" * 64)
+        assert not _build.is_current()
+    finally:
+        open(_build.STAMP_PATH, "w").write(stamp)

@@ -355,3 +355,30 @@ def test_torch_ops_dispatch_on_cuda():
     x = torch.rand(3, 50, device=dev())
     y = torch.ops.modfx.interp_linear(x, 120, True)
     assert np.array_equal(y.cpu().numpy(), oracle.linear_interpolate_last_dim(x.cpu().numpy(), 120))
+
+
+def test_torch_ops_of_the_whole_path_dispatch_on_cuda():
+    """every op of the path is reachable as torch.ops.modfx.* (CUDA key only)."""
+    import mod_extraction_b200._torch_ops  # noqa: F401
+    from mod_extraction_b200.models import LogMelSpectrogram
+    d = dev()
+    x = torch.from_numpy(white((2, 1, 4096), 9)).to(d)
+    mod = torch.rand(2, 4096, device=d)
+    y = torch.ops.modfx.tremolo(x, mod, torch.tensor([0.3, 0.9], device=d))
+    assert np.array_equal(y.cpu().numpy(), oracle.tremolo(x.cpu().numpy(), mod.cpu().numpy(), np.array([0.3, 0.9], np.float32)))
+    m = LogMelSpectrogram().to(d)
+    lm = torch.ops.modfx.logmel(x, m.window, m.fb_start, m.fb_count, m.fb_weight, m.fb_taps, 256, 1e-7)
+    assert torch.equal(lm, m(x))
+    mp = torch.ops.modfx.mel_power(x, m.window, m.fb_start, m.fb_count, m.fb_weight, m.fb_taps, 256, 1e-7)
+    assert float((torch.log(torch.clip(mp, min=1e-7)) - lm).abs().max()) <= 1e-5
+    sig = torch.from_numpy(np.stack([oracle.make_mod_signal(345, 172.5, 1.3, 0.4, "tri"),
+                                     oracle.make_mod_signal(345, 172.5, 2.1, 1.0, "cos")])).to(d)
+    top, bottom = torch.ops.modfx.find_corners(sig)
+    rt, rb = oracle.find_corners(sig.cpu().numpy())
+    assert np.array_equal(top.cpu().numpy(), rt) and np.array_equal(bottom.cpu().numpy(), rb)
+    sm = torch.ops.modfx.smoothen(sig, 8)
+    assert np.array_equal(sm.cpu().numpy(), oracle.smoothen(sig.cpu().numpy(), 8))
+    st = torch.ops.modfx.stretch_corners(sm, 10)
+    assert st.shape == sm.shape and torch.isfinite(st).all()
+    valid = torch.ops.modfx.check_mod_sig(sig, 1, 6, 1, 6, 34)
+    assert valid.shape == (2,)
