@@ -99,6 +99,19 @@ int modfx_flanger_chorus_f32(const float* x, float* y, int32_t B, int32_t C, int
                              modfx_param depth, modfx_param mix,
                              const int32_t* example_index, int32_t n_items, void* stream);
 
+/*
+ * The same delay line with first-order ALL-PASS instead of linear fractional-delay interpolation (north_star names
+ * "linear or all-pass"; the reference, fx.py:113, only has the linear blend -- this mode is this library's own
+ * definition, restated in oracle/modfx_oracle.c: it[n] = eta * (buf[q] - it[n-1]) + buf[p], eta = fr / (2 - fr)).
+ * Same arguments as modfx_flanger_chorus_f32; the modulation signal must come from memory (AUDIO_RATE / CONTROL_RATE).
+ */
+int modfx_flanger_chorus_allpass_f32(const float* x, float* y, int32_t B, int32_t C, int64_t N,
+                                     int32_t max_min_delay_samples, int32_t max_lfo_delay_samples,
+                                     const modfx_mod_source* mod,
+                                     modfx_param feedback, modfx_param min_delay_width, modfx_param width,
+                                     modfx_param depth, modfx_param mix,
+                                     const int32_t* example_index, int32_t n_items, void* stream);
+
 /* Replaces apply_tremolo, mod_extraction/fx.py:13-22. */
 int modfx_tremolo_f32(const float* x, float* y, int32_t B, int32_t C, int64_t N,
                       const modfx_mod_source* mod, modfx_param mix, void* stream);

@@ -58,6 +58,9 @@ _SIGNATURES = {
     "modfx_flanger_chorus_f32": ([_vp, _vp, _i32, _i32, _i64, _i32, _i32, ctypes.POINTER(ModfxModSource),
                                   ModfxParam, ModfxParam, ModfxParam, ModfxParam, ModfxParam, _vp, _i32, _vp],
                                  ctypes.c_int),
+    "modfx_flanger_chorus_allpass_f32": ([_vp, _vp, _i32, _i32, _i64, _i32, _i32, ctypes.POINTER(ModfxModSource),
+                                          ModfxParam, ModfxParam, ModfxParam, ModfxParam, ModfxParam, _vp, _i32, _vp],
+                                         ctypes.c_int),
     "modfx_tremolo_f32": ([_vp, _vp, _i32, _i32, _i64, ctypes.POINTER(ModfxModSource), ModfxParam, _vp], ctypes.c_int),
     "modfx_lfo_f32": ([_vp, _i32, _i64, ctypes.c_float, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "modfx_interp_linear_f32": ([_vp, _vp, _i64, _i64, _i64, _i32, _vp], ctypes.c_int),

@@ -114,9 +114,10 @@ class ModSource:
 
 def flanger_chorus(x: Tensor, mod: ModSource, m_min: int, m_lfo: int, feedback: Param, min_delay_width: Param,
                    width: Param, depth: Param, mix: Param, example_index: Optional[Tensor] = None,
-                   out: Optional[Tensor] = None) -> Tensor:
+                   out: Optional[Tensor] = None, interpolation: str = "linear") -> Tensor:
+    """interpolation: "linear" (the reference, fx.py:113) or "allpass" (own definition, include/modfx.h)."""
     _require_cuda(x, "x")
-    assert x.ndim == 3
+    assert x.ndim == 3 and interpolation in ("linear", "allpass")
     x = x.contiguous()
     B, C, N = x.shape
     y = torch.empty_like(x) if out is None else out
@@ -133,8 +134,9 @@ def flanger_chorus(x: Tensor, mod: ModSource, m_min: int, m_lfo: int, feedback: 
             idx_ptr, n_items = ctypes.c_void_p(idx.data_ptr()), idx.numel()
             if n_items == 0:
                 return y
-        _lib.check(_lib.lib().modfx_flanger_chorus_f32(_ptr(x), _ptr(y), B, C, N, m_min, m_lfo, ctypes.byref(src),
-                                                       *args, idx_ptr, n_items, _stream()))
+        L = _lib.lib()
+        fn = L.modfx_flanger_chorus_f32 if interpolation == "linear" else L.modfx_flanger_chorus_allpass_f32
+        _lib.check(fn(_ptr(x), _ptr(y), B, C, N, m_min, m_lfo, ctypes.byref(src), *args, idx_ptr, n_items, _stream()))
     return y
 
 

@@ -1090,6 +1090,76 @@ __global__ void __launch_bounds__(kCtaThreads) fc_cta_kernel(const FcArgs a, int
 #endif
 }
 
+// ---- all-pass fractional-delay interpolation (north_star: "per-sample linear or all-pass interpolation") -----------
+// The reference only has the linear blend of fx.py:113; this mode is this repository's OWN definition,
+// stated in include/modfx.h: the read position lies delta = 1 - fraction samples behind the newer tap q, and
+//   it[n] = eta * (buf[q] - it[n-1]) + buf[p],   eta = (1 - delta) / (1 + delta) = fraction / (2 - fraction)
+// replaces the blend; index arithmetic, feedback, mix and clip stay those of fx.py:95-118.  The interpolator carries
+// a state from sample to sample, so a delay line is serial whatever its delay: one LANE per delay line, up to 32 lines
+// per one-warp CTA, the written samples in a shared-memory ring laid out [time][line] (conflict-free), audio moved
+// through 32 x 32 transposing tiles so that global traffic stays coalesced.  A mode behind a flag, not the hot path.
+__global__ void __launch_bounds__(kWarp) fc_allpass_kernel(const FcArgs a, int L, int ring_mask, int n_lines) {
+    extern __shared__ __align__(16) float smem[];
+    float(*xt)[kWarp + 1] = reinterpret_cast<float(*)[kWarp + 1]>(smem);
+    float(*mt)[kWarp + 1] = reinterpret_cast<float(*)[kWarp + 1]>(smem + kWarp * (kWarp + 1));
+    float* ring = smem + 2 * kWarp * (kWarp + 1);           // [(ring_mask + 1)][L]
+    const int lane = threadIdx.x;
+    const int line = blockIdx.x * L + lane;                 // (item, channel)
+    const bool live = lane < L && line < n_lines;
+    const int item = live ? line / a.C : 0;
+    const int ch = live ? line - item * a.C : 0;
+    const int b = a.index ? a.index[item] : item;
+    const int N = a.N;
+    const Coef c = make_coef(a, b);
+    const float* xs = a.x + ((int64_t)b * a.C + ch) * (int64_t)N;
+    float* ys = a.y + ((int64_t)b * a.C + ch) * (int64_t)N;
+    const bool audio = a.n_lo == 0;
+    const float* ms = audio ? a.mod + (a.mod_has_ch ? ((int64_t)b * a.C + ch) : (int64_t)b) * (int64_t)N
+                            : a.mod + (int64_t)b * a.n_lo;
+    for (int i = lane; i < (ring_mask + 1) * L; i += kWarp) ring[i] = 0.0f;             // fx.py:92
+    __syncwarp();
+    float it_prev = 0.0f;
+    int wk = 0;
+    for (int n0 = 0; n0 < N; n0 += kWarp) {
+        for (int l = 0; l < L; ++l) {                       // line l's next 32 samples: one 128-byte request
+            const float* xr = reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(xs), l));
+            const float* mr = reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(ms), l));
+            const bool ok = __shfl_sync(kFull, (int)live, l) && (n0 + lane < N);
+            xt[l][lane] = ok ? xr[n0 + lane] : 0.0f;
+            if (audio) mt[l][lane] = ok ? mr[n0 + lane] : 0.0f;
+        }
+        __syncwarp();
+        if (live) {
+            const int cnt = min(kWarp, N - n0);
+            for (int i = 0; i < cnt; ++i) {
+                const int n = n0 + i;
+                const float m = audio ? mt[lane][i] : upsample_ac(ms, a.n_lo, a.up_scale, n);
+                float fr, omfr;
+                int kp;
+                fc_index(m, wk, c, fr, omfr, kp);                                       // fx.py:95-102
+                const float vp = ring[((n - kp) & ring_mask) * L + lane];
+                const float vq = ring[((n - kq_of(kp, c.M)) & ring_mask) * L + lane];
+                const float eta = __fdiv_rn(fr, __fsub_rn(2.0f, fr));
+                const float it = __fadd_rn(__fmul_rn(eta, __fsub_rn(vq, it_prev)), vp);
+                it_prev = it;
+                const float x = xt[lane][i];
+                ring[(n & ring_mask) * L + lane] = __fadd_rn(x, __fmul_rn(c.fb, it));   // fx.py:114
+                const float o = __fadd_rn(x, __fmul_rn(c.depth, it));                   // fx.py:115
+                const float r = __fadd_rn(__fmul_rn(c.omm, x), __fmul_rn(c.mix, o));    // fx.py:117
+                xt[lane][i] = fminf(fmaxf(r, -1.0f), 1.0f);                             // fx.py:118
+                if (++wk == c.M) wk = 0;
+            }
+        }
+        __syncwarp();
+        for (int l = 0; l < L; ++l) {
+            float* yr = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(ys), l));
+            const bool ok = __shfl_sync(kFull, (int)live, l) && (n0 + lane < N);
+            if (ok) yr[n0 + lane] = xt[l][lane];
+        }
+        __syncwarp();
+    }
+}
+
 // apply_tremolo, fx.py:13-22: ((1 - mix) * x) + ((mix * mod) * x); one block per (example, channel).
 template <int MODE>
 __global__ void __launch_bounds__(256) tremolo_kernel(const FcArgs a) {
@@ -1293,6 +1363,51 @@ extern "C" int modfx_flanger_chorus_f32(const float* x, float* y, int32_t B, int
     else if (mode == kControlRate) LAUNCH_FC(kControlRate);
     else LAUNCH_FC(kDirectLfo);
 #undef LAUNCH_FC
+    MODFX_CUDA_OK(cudaGetLastError());
+    return MODFX_OK;
+}
+
+extern "C" int modfx_flanger_chorus_allpass_f32(const float* x, float* y, int32_t B, int32_t C, int64_t N,
+                                                int32_t Mmin, int32_t Mlfo, const modfx_mod_source* mod,
+                                                modfx_param feedback, modfx_param min_delay_width, modfx_param width,
+                                                modfx_param depth, modfx_param mix, const int32_t* example_index,
+                                                int32_t n_items, void* stream) {
+    MODFX_REQUIRE(x && y, "x / y is NULL");
+    MODFX_REQUIRE(B >= 0 && C >= 1 && N >= 1 && N < (1ll << 30), "bad shape B=%d C=%d N=%lld", B, C, (long long)N);
+    MODFX_REQUIRE(Mmin >= 0 && Mlfo >= 0 && Mmin + Mlfo >= 1, "bad delay line Mmin=%d Mlfo=%d", Mmin, Mlfo);
+    int st;
+    if ((st = check_scalar(feedback, "feedback", false)) != MODFX_OK) return st;
+    if ((st = check_scalar(min_delay_width, "min_delay_width", true)) != MODFX_OK) return st;
+    if ((st = check_scalar(width, "width", true)) != MODFX_OK) return st;
+    if ((st = check_scalar(depth, "depth", true)) != MODFX_OK) return st;
+    if ((st = check_scalar(mix, "mix", true)) != MODFX_OK) return st;
+    FcArgs a{};
+    a.x = x; a.y = y; a.B = B; a.C = C; a.N = (int)N;
+    a.Mmin = Mmin; a.Mlfo = Mlfo; a.M = Mmin + Mlfo;
+    int mode = 0;
+    if ((st = fill_mod(a, mod, B, N, mode)) != MODFX_OK) return st;
+    if (mode == kDirectLfo || a.lfo_freq)
+        return fail(MODFX_ERR_UNSUPPORTED, "all-pass interpolation takes the modulation signal from memory (audio or control rate)");
+    if (mode == kAudioRate) a.n_lo = 0;
+    a.fb_p = feedback.dev;         a.fb_s = (float)feedback.value;
+    a.mdw_p = min_delay_width.dev; a.min_delay_s = (float)(min_delay_width.value * (double)Mmin);
+    a.width_p = width.dev;         a.lfo_delay_s = (float)((double)Mlfo * width.value);
+    a.depth_p = depth.dev;         a.depth_s = (float)depth.value;
+    a.mix_p = mix.dev;             a.mix_s = (float)mix.value; a.omm_s = (float)(1.0 - mix.value);
+    a.index = example_index;
+    a.n_items = example_index ? n_items : B;
+    if (a.n_items == 0) return MODFX_OK;
+    MODFX_REQUIRE(a.n_items > 0, "n_items=%d", a.n_items);
+    const int ring = next_pow2(a.M + 1);
+    a.ring_mask = ring - 1;
+    int L = kWarp;
+    while (L > 1 && (size_t)ring * L * sizeof(float) > 160 * 1024) L >>= 1;
+    const size_t smem = sizeof(float) * ((size_t)ring * L + 2 * kWarp * (kWarp + 1));
+    if (smem > 200 * 1024) return fail(MODFX_ERR_UNSUPPORTED, "delay line of %d samples exceeds shared memory", a.M);
+    const int n_lines = a.n_items * C;
+    if (smem > 48 * 1024)
+        MODFX_CUDA_OK(cudaFuncSetAttribute(fc_allpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fc_allpass_kernel<<<(unsigned)((n_lines + L - 1) / L), kWarp, smem, as_stream(stream)>>>(a, L, ring - 1, n_lines);
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
 }

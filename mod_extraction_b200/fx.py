@@ -90,8 +90,13 @@ class MonoFlangerChorusModule(nn.Module):
                  sr: float,
                  max_min_delay_ms: float,
                  max_lfo_delay_ms: float,
-                 check_ranges: bool = True) -> None:
+                 check_ranges: bool = True,
+                 interpolation: str = "linear") -> None:
         super().__init__()
+        # "linear" is the reference (fx.py:113); "allpass" is an addition with no reference counterpart:
+        # first-order all-pass fractional-delay interpolation, defined in include/modfx.h
+        assert interpolation in ("linear", "allpass")
+        self.interpolation = interpolation
         self.batch_size = batch_size
         self.n_ch = n_ch
         self.n_samples = n_samples
@@ -124,7 +129,7 @@ class MonoFlangerChorusModule(nn.Module):
     def _render(self, x: Tensor, mod: ModSource, feedback, min_delay_width, width, depth, mix,
                 example_index: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
         return _ops.flanger_chorus(x, mod, self.max_min_delay_samples, self.max_lfo_delay_samples,
-                                   feedback, min_delay_width, width, depth, mix, example_index, out)
+                                   feedback, min_delay_width, width, depth, mix, example_index, out, self.interpolation)
 
     # ------------------------------------------------------------------ reference API
     def apply_effect(self,

@@ -100,6 +100,7 @@ typedef struct {
     const float* x; const float* mod; int mod_has_ch; float* y;
     int B, C; int64_t N; int Mmin, Mlfo;
     const float *lfo_delay, *min_delay, *fb, *depth, *mix, *one_minus_mix;
+    int interp;     /* 0: linear (the reference, fx.py:113); 1: first-order all-pass interpolation (OWN definition, see below) */
 } fc_ctx;
 
 static void fc_item(int bc, void* vctx) {
@@ -114,6 +115,7 @@ static void fc_item(int bc, void* vctx) {
     float* buf = (float*)calloc((size_t)M, sizeof(float));          /* fx.py:92 */
     const float a = k->lfo_delay[b], d0 = k->min_delay[b];
     const float g = k->fb[b], dp = k->depth[b], mx = k->mix[b], omm = k->one_minus_mix[b];
+    float it_prev = 0.0f;                           /* all-pass interpolator state (interp == 1) */
     for (int64_t n = 0; n < N; ++n) {
         const int w = (int)(n % M);                                  /* fx.py:95 */
         float d = a * ms[n];                                         /* fx.py:98 */
@@ -127,10 +129,24 @@ static void fc_item(int bc, void* vctx) {
         if (p < 0) p = 0;
         if (p >= M) p = M - 1;        /* reference would raise in gather; stay memory-safe */
         const int q = (p + 1) % M;                                   /* fx.py:102 */
-        const float t1 = fr * buf[q];                                /* fx.py:113 */
-        const float omf = 1.0f - fr;
-        const float t2 = omf * buf[p];
-        const float it = t1 + t2;
+        float it;
+        if (k->interp == 0) {
+            const float t1 = fr * buf[q];                            /* fx.py:113 */
+            const float omf = 1.0f - fr;
+            const float t2 = omf * buf[p];
+            it = t1 + t2;
+        } else {
+            /* OWN definition (the reference has linear interpolation only): the read position lies
+             * delta = 1 - fr samples behind the newer tap buf[q]; first-order all-pass fractional delay
+             *   it[n] = eta * (buf[q] - it[n-1]) + buf[p],  eta = (1 - delta) / (1 + delta) = fr / (2 - fr)
+             * (J. O. Smith, "Physical Audio Signal Processing", all-pass interpolation), everything else as fx.py:95-118. */
+            const float den = 2.0f - fr;
+            const float eta = fr / den;
+            const float dq = buf[q] - it_prev;
+            const float e1 = eta * dq;
+            it = e1 + buf[p];
+            it_prev = it;
+        }
         const float xn = xs[n];
         const float f1 = g * it;                                     /* fx.py:114 */
         buf[w] = xn + f1;
@@ -152,7 +168,19 @@ void modfx_oracle_flanger_chorus(const float* x, const float* mod, int mod_has_c
                                  const float* fb, const float* depth,
                                  const float* mix, const float* one_minus_mix) {
     fc_ctx k = { x, mod, mod_has_ch, y, B, C, N, Mmin, Mlfo,
-                 lfo_delay, min_delay, fb, depth, mix, one_minus_mix };
+                 lfo_delay, min_delay, fb, depth, mix, one_minus_mix, 0 };
+    parallel_for(B * C, fc_item, &k);
+}
+
+/* Same delay line with all-pass instead of linear fractional-delay interpolation (north_star "linear or all-pass";
+ * no reference implementation exists: this float32 restatement is this repository's OWN definition). */
+void modfx_oracle_flanger_chorus_allpass(const float* x, const float* mod, int mod_has_ch, float* y,
+                                         int B, int C, int64_t N, int Mmin, int Mlfo,
+                                         const float* lfo_delay, const float* min_delay,
+                                         const float* fb, const float* depth,
+                                         const float* mix, const float* one_minus_mix) {
+    fc_ctx k = { x, mod, mod_has_ch, y, B, C, N, Mmin, Mlfo,
+                 lfo_delay, min_delay, fb, depth, mix, one_minus_mix, 1 };
     parallel_for(B * C, fc_item, &k);
 }
 

@@ -58,6 +58,8 @@ def lib() -> ctypes.CDLL:
         ci = ctypes.c_int
         L.modfx_oracle_flanger_chorus.argtypes = [fp, fp, ci, fp, ci, ci, i64, ci, ci] + [fp] * 6
         L.modfx_oracle_flanger_chorus.restype = None
+        L.modfx_oracle_flanger_chorus_allpass.argtypes = L.modfx_oracle_flanger_chorus.argtypes
+        L.modfx_oracle_flanger_chorus_allpass.restype = None
         L.modfx_oracle_tremolo.argtypes = [fp, fp, ci, fp, ci, ci, i64, fp, fp]
         L.modfx_oracle_tremolo.restype = None
         L.modfx_oracle_lfo.argtypes = [fp, i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ci,
@@ -137,8 +139,11 @@ def derived_fc_params(B: int, m_min: int, m_lfo: int, feedback: Param, min_delay
 def flanger_chorus(x: np.ndarray, mod_sig: np.ndarray, feedback: Param = 0.0,
                    min_delay_width: Param = 1.0, width: Param = 1.0, depth: Param = 1.0,
                    mix: Param = 1.0, *, sr: float = 44100.0, max_min_delay_ms: float,
-                   max_lfo_delay_ms: float) -> np.ndarray:
-    """MonoFlangerChorusModule.forward, fx.py:121-130 (ctor fx.py:26-44)."""
+                   max_lfo_delay_ms: float, interpolation: str = "linear") -> np.ndarray:
+    """MonoFlangerChorusModule.forward, fx.py:121-130 (ctor fx.py:26-44).
+    interpolation="allpass": the same delay line with a first-order all-pass fractional-delay interpolator -- OWN
+    definition (the reference only has the linear one), see modfx_oracle.c."""
+    assert interpolation in ("linear", "allpass")
     x = _f32(x)
     assert x.ndim == 3
     B, C, N = x.shape
@@ -148,8 +153,35 @@ def flanger_chorus(x: np.ndarray, mod_sig: np.ndarray, feedback: Param = 0.0,
     m_min, m_lfo = delay_samples(sr, max_min_delay_ms, max_lfo_delay_ms)
     coefs = derived_fc_params(B, m_min, m_lfo, feedback, min_delay_width, width, depth, mix)
     y = np.empty_like(x)
-    lib().modfx_oracle_flanger_chorus(_ptr(x), _ptr(mod_sig), has_ch, _ptr(y), B, C, N, m_min, m_lfo,
-                                      *[_ptr(c) for c in coefs])
+    fn = lib().modfx_oracle_flanger_chorus if interpolation == "linear" else lib().modfx_oracle_flanger_chorus_allpass
+    fn(_ptr(x), _ptr(mod_sig), has_ch, _ptr(y), B, C, N, m_min, m_lfo, *[_ptr(c) for c in coefs])
+    return y
+
+
+def flanger_chorus_allpass_f64(x: np.ndarray, mod_sig: np.ndarray, feedback: float, min_delay_width: float, width: float,
+                               depth: float, mix: float, *, sr: float = 44100.0, max_min_delay_ms: float,
+                               max_lfo_delay_ms: float) -> np.ndarray:
+    """The all-pass variant in float64, one (N,) clip, scalar parameters, python loop (small cases only): the
+    "what it should compute" restatement of this repository's OWN definition."""
+    x = np.asarray(x, dtype=np.float64)
+    mod = np.asarray(mod_sig, dtype=np.float64)
+    m_min, m_lfo = delay_samples(sr, max_min_delay_ms, max_lfo_delay_ms)
+    M = m_min + m_lfo
+    buf = np.zeros(M)
+    y = np.empty_like(x)
+    it_prev = 0.0
+    for n in range(x.shape[0]):
+        w = n % M
+        d = (m_lfo * width) * mod[n] + min_delay_width * m_min
+        r = ((w - d) + M) % M
+        p = int(math.floor(r))
+        fr = r - p
+        p = min(max(p, 0), M - 1)
+        q = (p + 1) % M
+        it = fr / (2.0 - fr) * (buf[q] - it_prev) + buf[p]
+        it_prev = it
+        buf[w] = x[n] + feedback * it
+        y[n] = min(max((1.0 - mix) * x[n] + mix * (x[n] + depth * it), -1.0), 1.0)
     return y
 
 

@@ -382,3 +382,42 @@ def test_torch_ops_of_the_whole_path_dispatch_on_cuda():
     assert st.shape == sm.shape and torch.isfinite(st).all()
     valid = torch.ops.modfx.check_mod_sig(sig, 1, 6, 1, 6, 34)
     assert valid.shape == (2,)
+
+
+@pytest.mark.parametrize("mmd,mld", [(1.0, 10.0), (30.0, 10.0)])
+def test_allpass_interpolation_mode_matches_own_restatement(mmd, mld):
+    """north_star names "linear or all-pass" interpolation; the reference only has linear, so this mode is
+    checked against this repository's OWN restatements: bit-exact against the float32 one (same operation order), and
+    against the float64 python loop on a short clip within 1e-4 on >= 99 % of the samples with an SNR >= 40 dB (where
+    the delay passes an integer number of samples, float32 and float64 index arithmetic pick different taps for a
+    sample -- the same input sensitivity as SURVEY F3 -- and the interpolator's state carries the difference on)."""
+    from tests.helpers import snr_db
+    from mod_extraction_b200.fx import MonoFlangerChorusModule
+    rng = np.random.RandomState(17)
+    B, C, N = 5, 2, 6000
+    x = white((B, C, N), 18) * np.float32(0.4)
+    lo = _lfo_lo(B, rng, n_lo=N // 100, sr_lo=441.0)
+    params = _rand_params(B, rng)
+    mod = oracle.linear_interpolate_last_dim(lo, N)
+    ref = oracle.flanger_chorus(x, mod, *params, max_min_delay_ms=mmd, max_lfo_delay_ms=mld, interpolation="allpass")
+    m = MonoFlangerChorusModule(B, C, N, SR, mmd, mld, interpolation="allpass")
+    xd = torch.from_numpy(x).to(dev())
+    y_audio = m(xd, torch.from_numpy(mod).to(dev()), *[to_t(p) for p in params]).cpu().numpy()
+    y_ctrl = m.forward_control_rate(xd, torch.from_numpy(lo).to(dev()), *[to_t(p) for p in params]).cpu().numpy()
+    assert np.array_equal(y_audio, ref) and np.array_equal(y_ctrl, ref)
+    f64 = oracle.flanger_chorus_allpass_f64(x[0, 0, :3000], mod[0, :3000], *[float(p[0]) for p in params],
+                                            max_min_delay_ms=mmd, max_lfo_delay_ms=mld)
+    e64 = np.abs(y_audio[0, 0, :3000] - f64)
+    assert (e64 <= 1e-4).mean() >= 0.99 and snr_db(f64, y_audio[0, 0, :3000]) >= 40.0, (e64.max(), (e64 <= 1e-4).mean())
+    # it is a different interpolator, not a different effect: close to the linear rendering, not equal to it
+    lin = oracle.flanger_chorus(x, mod, *params, max_min_delay_ms=mmd, max_lfo_delay_ms=mld)
+    assert not np.array_equal(lin, ref) and np.corrcoef(lin.ravel(), ref.ravel())[0, 1] > 0.9
+    # subsets and many lines (more than one CTA of 32 delay lines)
+    B2 = 40
+    x2 = white((B2, 1, 2000), 19)
+    mod2 = rng.uniform(0, 1, (B2, 2000)).astype(np.float32)
+    p2 = _rand_params(B2, rng)
+    ref2 = oracle.flanger_chorus(x2, mod2, *p2, max_min_delay_ms=mmd, max_lfo_delay_ms=mld, interpolation="allpass")
+    m2 = MonoFlangerChorusModule(B2, 1, 2000, SR, mmd, mld, interpolation="allpass")
+    y2 = m2(torch.from_numpy(x2).to(dev()), torch.from_numpy(mod2).to(dev()), *[to_t(p) for p in p2]).cpu().numpy()
+    assert np.array_equal(y2, ref2)
