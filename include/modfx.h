@@ -243,6 +243,18 @@ int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, c
                      void* workspace, void* stream);
 
 /*
+ * The DSP of one batch of PedalboardPhaserDataset.__getitem__, mod_extraction/datasets.py:428-453: row b of x holds
+ * proc_n = n_out + round(sr / rate_hz[b]) samples ("one extra LFO period", rows padded to the common pitch N); the
+ * phaser runs over the row from its first sample and the window [start[b], start[b] + n_out) of the wet signal AND of
+ * the dry input is delivered (datasets.py:445-447): y (B, n_out), dry_out (B, n_out) or NULL.  Samples past the window
+ * are never processed (the effect is causal).  Needs a host block size that is a multiple of 128 samples.
+ */
+int modfx_phaser_crop_f32(const float* x, float* y, float* dry_out, int32_t B, int64_t N, int64_t n_out,
+                          const int32_t* start, float sr, const float* rate_hz, const float* depth,
+                          const float* centre_hz, const float* feedback, const float* mix, int32_t block,
+                          const int32_t* example_index, int32_t n_items, void* workspace, void* stream);
+
+/*
  * LFO-net body behind the log-mel front end: Spectral2DCNN.cnn, the mean over
  * mel bins, the 1x1 output convolution and the sigmoid, mod_extraction/models.py:183-195,209-214.
  * Activations between layers are channels-last float32: (B, H, W, C) with H = mel bins, W = frames.

@@ -215,6 +215,32 @@ def phaser(x: Tensor, sr: float, rate_hz: Tensor, depth: Tensor, centre_hz: Tens
     return y
 
 
+def phaser_crop(x: Tensor, n_out: int, start: Tensor, sr: float, rate_hz: Tensor, depth: Tensor, centre_hz: Tensor,
+                feedback: Tensor, mix: Tensor, block: int = 8192, want_dry: bool = True):
+    """x: (B, N) CUDA float32 rows of (at least) start[b] + n_out samples.  Returns (wet (B, n_out), dry (B, n_out) or None):
+    the phaser over each row from its first sample, delivered on the window [start[b], start[b] + n_out)
+    (PedalboardPhaserDataset.__getitem__, datasets.py:436-447)."""
+    _require_cuda(x, "x")
+    assert x.ndim == 2
+    x = x.contiguous()
+    B, N = x.shape
+    y = torch.empty((B, n_out), device=x.device, dtype=torch.float32)
+    dry = torch.empty((B, n_out), device=x.device, dtype=torch.float32) if want_dry else None
+    keep = _Keep()
+    with torch.cuda.device(x.device):
+        ps = [keep(torch.as_tensor(p).detach().to(device=x.device, dtype=torch.float32).reshape(-1).contiguous())
+              for p in (rate_hz, depth, centre_hz, feedback, mix)]
+        assert all(t.shape == (B,) for t in ps)
+        st = keep(torch.as_tensor(start).to(device=x.device, dtype=torch.int32).reshape(-1).contiguous())
+        assert st.shape == (B,)
+        L = _lib.lib()
+        ws = keep(torch.empty((max(1, int(L.modfx_phaser_workspace_bytes(B, N))),), device=x.device, dtype=torch.uint8))
+        _lib.check(L.modfx_phaser_crop_f32(_ptr(x), _ptr(y), _ptr(dry), B, N, n_out, _ptr(st), float(sr),
+                                           *[_ptr(t) for t in ps], int(block), ctypes.c_void_p(0), 0, _ptr(ws), _stream()))
+        ws.record_stream(torch.cuda.current_stream(x.device))
+    return y, dry
+
+
 def find_corners(mod_sig: Tensor):
     """(rows, n) CUDA float32 -> (top, bottom) uint8 flags (modulations.py:219-238)."""
     _require_cuda(mod_sig, "mod_sig")

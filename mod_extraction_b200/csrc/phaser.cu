@@ -17,6 +17,8 @@
 // K1 and K3 stage audio through shared memory so global traffic stays coalesced.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace modfx {
 namespace {
 
@@ -429,6 +431,364 @@ __global__ void __launch_bounds__(32 * kRunWarps) phaser_run_kernel(const Phaser
     }
 }
 
+// =====================================================================================================================
+// Single-pass fused phaser (the default path): one kernel reads the audio once and writes the result once.
+//
+// The four-kernel pipeline above moves 2.3x the algorithmic bytes (the audio is read twice, the control-rate coefficients
+// and the per-chunk maps round-trip HBM).  Here a CTA owns one SEGMENT of 4096 samples of one example and does everything
+// for it out of shared memory:
+//   A  the segment's audio lands in shared memory (one coalesced pass); the float32 oscillator phases of its 1024
+//      control points are walked chunk by chunk from chunk-start phases (phaser_phase_kernel below: a few bytes per
+//      128 samples, the only thing that is precomputed) -- sequential adds with the wrap at 2 pi, like the restatement;
+//   B  the transcendental map phase -> all-pass coefficient c = 2G - 1, all threads;
+//   C  per 64-sample sub-chunk the 7 unit-state runs + the zero-state run (two runs per thread, packed FFMA2) give its
+//      affine map; lanes = sub-chunks, so a warp's 32 lanes walk 32 different sub-chunks (padded rows: no conflicts);
+//   D  the state at the segment start comes from the CTA of the previous segment of the same example through global
+//      memory (decoupled look-back: CTAs take their (segment, example) from an atomic ticket in segment-major order, so a
+//      predecessor always holds an earlier ticket and is running or done: no deadlock); 8 lanes chain the 64 maps, the
+//      exit state is published for the next segment at once;
+//   E  64 threads re-run their sub-chunk from its true entry state, mix, clip;
+//   F  coalesced store -- optionally only the window [start[b], start[b] + n_out) of the row, together with the same
+//      window of the dry input: the random crop of PedalboardPhaserDataset.__getitem__ (datasets.py:445-447).
+// Segments past the last needed sample are never touched.  HBM traffic: 4 B in + 4 B out per sample + 64 B per segment.
+constexpr int kSegChunks = 32;                       // 128-sample chunks per segment
+constexpr int kSeg = kSegChunks * kChunk;            // 4096 samples
+constexpr int kSub = 64;                             // samples per scan sub-chunk
+constexpr int kSubs = kSeg / kSub;                   // 64 sub-chunks per segment
+constexpr int kSubCtl = kSub / kUpd;                 // 16 control points per sub-chunk
+constexpr int kSegCtl = kSeg / kUpd;                 // 1024
+constexpr int kFusedThreads = 256;
+constexpr int kRec = 8;                              // published state record: w1..w6, lastOutput, c the states are scaled for
+
+struct FusedArgs {
+    PhaserArgs a;
+    const int32_t* start;       // (B,) first delivered sample of each row, or nullptr (0)
+    int n_out;                  // delivered samples per row
+    float* dry_out;             // (B, n_out) window of the dry input, or nullptr
+    int n_seg;
+    int* ticket;                // 1 int, zero at launch
+    int* flags;                 // (n_items, n_seg), zero at launch
+    float* rec;                 // (n_items, n_seg, kRec)
+    float2* ph;                 // (n_items, n_chunks): phase at the chunk's first control point, phase of the one before
+};
+
+// chunk-start phases: one thread per (example, host block), juce::dsp::Oscillator semantics (see phaser_ctl_kernel)
+__global__ void __launch_bounds__(128) phaser_phase_kernel(const FusedArgs f, int n_blocks) {
+    const PhaserArgs& a = f.a;
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= a.n_items * n_blocks) return;
+    const int item = pair / n_blocks, blk = pair - item * n_blocks;
+    const int b = example_of(a, item);
+    const int need = f.start ? min(a.N, f.start[b] + f.n_out) : a.N;
+    if ((int64_t)blk * a.block >= need) return;
+    const float two_pi = MODFX_TWO_PI_F;
+    const float sr_down = (float)((double)a.sr / (double)kUpd);
+    const float inc = a.rate[b] * (two_pi / sr_down);
+    float p = 0.0f;
+    for (int i = 0; i < blk; ++i) {                  // whole blocks before this one: phase.advance(freq * n_down)
+        float next = p + inc * (float)(a.block / kUpd);
+        while (next >= two_pi) next -= two_pi;
+        p = next;
+    }
+    const int s0 = blk * a.block, s1 = min(s0 + a.block, a.N);
+    const int c0 = s0 / kChunk, c1 = (s1 + kChunk - 1) / kChunk;
+    float2* out = f.ph + (int64_t)item * a.n_chunks;
+    // the control point before this block's first one is the previous block's last: redo that block's walk (the same
+    // sequence of float32 additions its own thread performs, so the value is bit-identical); a clip's very first
+    // control point has no predecessor and the value is unused (all filter states are zero there)
+    float prev = 0.0f;
+    if (blk > 0) {
+        float q = 0.0f;
+        for (int i = 0; i < blk - 1; ++i) {
+            float next = q + inc * (float)(a.block / kUpd);
+            while (next >= two_pi) next -= two_pi;
+            q = next;
+        }
+        for (int j = 0; j < a.block / kUpd - 1; ++j) {
+            float next = q + inc;
+            while (next >= two_pi) next -= two_pi;
+            q = next;
+        }
+        prev = q;
+    }
+    for (int c = c0; c < c1; ++c) {
+        out[c] = make_float2(p, prev);
+        for (int j = 0; j < kCtl; ++j) {
+            prev = p;
+            float next = p + inc;
+            while (next >= two_pi) next -= two_pi;
+            p = next;
+        }
+    }
+}
+
+__device__ __forceinline__ float phaser_coef(float phase, float vol, float ctr, float log_span, float log_min, float w0) {
+    float lfo = sinf(phase - MODFX_PI_F) * vol + ctr;
+    lfo = fminf(fmaxf(lfo, 0.0f), 1.0f);
+    const float fc = exp10f(lfo * log_span + log_min);                   // mapToLog10
+    const float g = tanf(w0 * fc);                                       // TPT prewarp
+    return 2.0f * (g / (1.0f + g)) - 1.0f;
+}
+
+__global__ void __launch_bounds__(kFusedThreads) phaser_fused_kernel(const FusedArgs f) {
+    extern __shared__ __align__(16) float sm[];
+    float(*xs)[kSub + 1] = reinterpret_cast<float(*)[kSub + 1]>(sm);                        // [64][65] audio, then output
+    float(*cs)[kSubCtl + 1] = reinterpret_cast<float(*)[kSubCtl + 1]>(sm + kSubs * (kSub + 1));   // [64][17] col 0: coefficient before
+    float(*Ms)[kMapFloats + 1] = reinterpret_cast<float(*)[kMapFloats + 1]>(sm + kSubs * (kSub + 1) + kSubs * (kSubCtl + 1));   // [64][57]
+    float(*Ss)[kSFloats] = reinterpret_cast<float(*)[kSFloats]>(sm + kSubs * (kSub + 1) + kSubs * (kSubCtl + 1) + kSubs * (kMapFloats + 1));
+    float* phs = reinterpret_cast<float*>(Ms);                           // [1024 + 1] phases (dead before the maps are written)
+    __shared__ int tile_s;
+    __shared__ float entry[kRec];
+    const PhaserArgs& a = f.a;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) tile_s = atomicAdd(f.ticket, 1);
+    __syncthreads();
+    const int tile = tile_s;
+    const int seg = tile / a.n_items, item = tile - seg * a.n_items;     // segment-major: predecessors hold earlier tickets
+    const int b = example_of(a, item);
+    const int start = f.start ? f.start[b] : 0;
+    const int need = min(a.N, start + f.n_out);
+    const int n_base = seg * kSeg;
+    if (n_base >= need) return;
+    const float* xr = a.x + (int64_t)b * a.N;
+
+    // ---- A: audio + oscillator phases
+    const bool vec = ((reinterpret_cast<uintptr_t>(xr) & 15) == 0) && (n_base + kSeg <= a.N);
+    if (vec) {                                                            // 16-byte loads, 4 per thread
+#pragma unroll
+        for (int k = 0; k < kSeg / 4 / kFusedThreads; ++k) {
+            const int i4 = tid + k * kFusedThreads;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + n_base) + i4);
+            float* d = &xs[i4 >> 4][(i4 & 15) << 2];
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int i = tid; i < kSeg; i += kFusedThreads) {
+            const int n = n_base + i;
+            xs[i / kSub][i % kSub] = (n < a.N) ? __ldg(xr + n) : 0.0f;
+        }
+    }
+    const float two_pi = MODFX_TWO_PI_F;
+    if (tid < kSegChunks) {
+        const int chunk = seg * kSegChunks + tid;
+        const float sr_down = (float)((double)a.sr / (double)kUpd);
+        const float inc = a.rate[b] * (two_pi / sr_down);
+        float2 pp = (chunk < a.n_chunks) ? f.ph[(int64_t)item * a.n_chunks + chunk] : make_float2(0.0f, 0.0f);
+        if (tid == 0) phs[0] = pp.y;                                      // control point before the segment
+        float p = pp.x;
+#pragma unroll 4
+        for (int q = 0; q < kCtl; ++q) {
+            phs[1 + tid * kCtl + q] = p;
+            float next = p + inc;
+            while (next >= two_pi) next -= two_pi;
+            p = next;
+        }
+    }
+    __syncthreads();
+    // ---- B: phase -> all-pass coefficient
+    {
+        const float f_lo = 20.0f;
+        const double f_hi_d = (0.49 * (double)a.sr < 20000.0) ? 0.49 * (double)a.sr : 20000.0;
+        const float log_min = log10f(f_lo), log_span = log10f((float)f_hi_d) - log_min;
+        const float w0 = MODFX_PI_F / a.sr;
+        const float vol = a.depth[b] * 0.5f;
+        const float ctr = (log10f(a.centre[b]) - log_min) / log_span;
+        float cv[(kSegCtl + 1 + kFusedThreads - 1) / kFusedThreads];
+#pragma unroll
+        for (int k = 0; k < (kSegCtl + 1 + kFusedThreads - 1) / kFusedThreads; ++k) {
+            const int j = tid + k * kFusedThreads;                        // j = 0: the control point before the segment
+            cv[k] = (j <= kSegCtl) ? phaser_coef(phs[j], vol, ctr, log_span, log_min, w0) : 0.0f;
+        }
+        __syncthreads();                                                  // phs aliases Ms: all reads done before cs / Ms are written
+#pragma unroll
+        for (int k = 0; k < (kSegCtl + 1 + kFusedThreads - 1) / kFusedThreads; ++k) {
+            const int j = tid + k * kFusedThreads;
+            if (j <= kSegCtl) {
+                if (j >= 1) cs[(j - 1) / kSubCtl][1 + (j - 1) % kSubCtl] = cv[k];
+                if (j % kSubCtl == 0 && j < kSegCtl) cs[j / kSubCtl][0] = cv[k];     // coefficient before sub-chunk j / 16
+            }
+        }
+    }
+    __syncthreads();
+    const float fbk = a.feedback[b];
+    // ---- C: affine map of every sub-chunk (runs 2p, 2p+1 per thread; run 6 = unit lastOutput, run 7 = zero state + audio)
+    {
+        const int pair = warp >> 1, sc = ((warp & 1) << 5) | lane;
+        float2 s[kStagesAP];
+#pragma unroll
+        for (int k = 0; k < kStagesAP; ++k) s[k] = make_float2((2 * pair == k) ? 1.0f : 0.0f, (2 * pair + 1 == k) ? 1.0f : 0.0f);
+        float2 out_prev = make_float2(0.0f, 0.0f);
+        const float2 nfb = make_float2(-fbk, -fbk);
+        float c_cur = cs[sc][0];
+        int g0 = 0;
+        if (pair == 3) {
+            // unit lastOutput = out_prev of 1 / feedback: fed as u = -1 by hand for the first sample (finite for feedback 0);
+            // both runs start with zero all-pass states, so nothing to retune before the first control group
+            const float c0 = cs[sc][1];
+            out_prev = cascade_step2(make_float2(-1.0f, xs[sc][0]), s, c0);
+#pragma unroll
+            for (int q = 1; q < kUpd; ++q)
+                out_prev = cascade_step2(__ffma2_rn(nfb, out_prev, make_float2(0.0f, xs[sc][q])), s, c0);
+            c_cur = c0;
+            g0 = 1;
+        }
+#pragma unroll 2
+        for (int g = g0; g < kSubCtl; ++g) {
+            const float c = cs[sc][1 + g];
+            cascade_retune2(s, c_cur, c);
+            c_cur = c;
+#pragma unroll
+            for (int q = 0; q < kUpd; ++q) {
+                const float2 u = (pair == 3) ? __ffma2_rn(nfb, out_prev, make_float2(0.0f, xs[sc][g * kUpd + q]))
+                                             : __fmul2_rn(nfb, out_prev);
+                out_prev = cascade_step2(u, s, c);
+            }
+        }
+        float* m = &Ms[sc][2 * pair * kState];
+#pragma unroll
+        for (int k = 0; k < kStagesAP; ++k) {
+            m[k] = s[k].x;
+            m[kState + k] = s[k].y;
+        }
+        m[6] = out_prev.x * fbk;
+        m[kState + 6] = out_prev.y * fbk;
+    }
+    __syncthreads();
+    // ---- D: entry state of the segment (look-back), entry state of every sub-chunk, exit state published.
+    // Three short passes instead of one chain of 64 dependent steps: (1) every warp composes the 8 maps of its group
+    // into one, all groups at once; (2) warp 0 takes the segment's entry state from the previous segment's CTA and
+    // chains the 8 group maps; (3) every warp chains its 8 sub-chunks from its group's entry state.
+    float(*GM)[kMapFloats + 1] = reinterpret_cast<float(*)[kMapFloats + 1]>(Ss + kSubs);       // [8][57] group maps
+    float(*GS)[kSFloats] = reinterpret_cast<float(*)[kSFloats]>(reinterpret_cast<float*>(GM) + 8 * (kMapFloats + 1));   // [8][8]
+    {
+        // (1) lane = (row i = lane >> 3 and i + 4, column r = lane & 7) of the running product [Phi | z]
+        const int r = lane & 7, i0 = lane >> 3, i1 = i0 + 4;
+        float* g = GM[warp];
+        {
+            const float* m = Ms[warp * 8];
+            g[r * kState + i0] = m[r * kState + i0];
+            if (i1 < kState) g[r * kState + i1] = m[r * kState + i1];
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 1; k < 8; ++k) {
+            const float* m = Ms[warp * 8 + k];
+            float a0 = (r == 7) ? m[7 * kState + i0] : 0.0f;
+            float a1 = (r == 7 && i1 < kState) ? m[7 * kState + i1] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < kState; ++j) {
+                const float cj = g[r * kState + j];
+                a0 = fmaf(m[j * kState + i0], cj, a0);
+                if (i1 < kState) a1 = fmaf(m[j * kState + i1], cj, a1);
+            }
+            __syncwarp();
+            g[r * kState + i0] = a0;
+            if (i1 < kState) g[r * kState + i1] = a1;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float* rec = f.rec + ((int64_t)item * f.n_seg + seg) * kRec;
+        if (seg > 0) {
+            const int* flag = f.flags + (int64_t)item * f.n_seg + seg - 1;
+            if (lane == 0) {
+                while (atomicAdd(const_cast<int*>(flag), 0) == 0) __nanosleep(64);
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane < kRec) entry[lane] = __ldcg(rec - kRec + lane);
+        } else if (lane < kRec) {
+            entry[lane] = 0.0f;
+        }
+        __syncwarp();
+        // (2) the predecessor left its all-pass states scaled for ITS last coefficient, which is this segment's cs[0][0]
+        const int i = lane & 7, ii = (i < kState) ? i : 0;
+        float sv = (i < kState) ? entry[i] : 0.0f;
+        if (lane < 8) {
+#pragma unroll 1
+            for (int gq = 0; gq < 8; ++gq) {
+                GS[gq][i] = sv;
+                const float* m = GM[gq];
+                float acc = m[7 * kState + ii];
+#pragma unroll
+                for (int r = 0; r < kState; ++r) acc = fmaf(m[r * kState + ii], __shfl_sync(0xffu, sv, r, 8), acc);
+                sv = (i < kState) ? acc : 0.0f;
+            }
+            if (i < kState) rec[i] = sv;
+            else rec[7] = cs[kSubs - 1][kSubCtl];
+            __threadfence();
+        }
+        __syncwarp();
+        if (lane == 0) atomicExch(f.flags + (int64_t)item * f.n_seg + seg, 1);
+    }
+    // the window of the dry input goes out while warp 0 chains (xs still holds the audio)
+    if (f.dry_out) {
+        float* dr = f.dry_out + (int64_t)b * f.n_out;
+        for (int i = tid; i < kSeg; i += kFusedThreads) {
+            const int idx = n_base + i - start;
+            if (idx >= 0 && idx < f.n_out && n_base + i < a.N) dr[idx] = xs[i / kSub][i % kSub];
+        }
+    }
+    __syncthreads();
+    // (3) entry state of every sub-chunk: each warp chains its group (8 lanes, lane i < 7 owns state component i)
+    if (lane < 8) {
+        const int i = lane, ii = (i < kState) ? i : 0;
+        float sv = (i < kState) ? GS[warp][i] : 0.0f;
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+            const int sc = warp * 8 + k;
+            Ss[sc][i] = sv;
+            const float* m = Ms[sc];
+            float acc = m[7 * kState + ii];
+#pragma unroll
+            for (int r = 0; r < kState; ++r) acc = fmaf(m[r * kState + ii], __shfl_sync(0xffu, sv, r, 8), acc);
+            sv = (i < kState) ? acc : 0.0f;
+        }
+    }
+    __syncthreads();
+    // ---- E: re-run every sub-chunk from its true entry state, mix and clip (datasets.py:472)
+    if (tid < kSubs) {
+        const int sc = tid;
+        float s[kStagesAP];
+#pragma unroll
+        for (int k = 0; k < kStagesAP; ++k) s[k] = Ss[sc][k];
+        float last = Ss[sc][6];
+        const float wet = a.mix[b], dry = 1.0f - a.mix[b];
+        float c_cur = cs[sc][0];
+#pragma unroll 2
+        for (int g = 0; g < kSubCtl; ++g) {
+            const float c = cs[sc][1 + g];
+            cascade_retune(s, c_cur, c);
+            c_cur = c;
+#pragma unroll
+            for (int q = 0; q < kUpd; ++q) {
+                const float in = xs[sc][g * kUpd + q];
+                const float out = cascade_step(in - last, s, c);
+                last = out * fbk;
+                xs[sc][g * kUpd + q] = fminf(fmaxf(fmaf(wet, out, dry * in), -1.0f), 1.0f);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- F: coalesced store of the delivered window
+    float* yr = a.y + (int64_t)b * f.n_out;
+    if (vec && start == 0 && n_base + kSeg <= f.n_out && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0)) {
+#pragma unroll
+        for (int k = 0; k < kSeg / 4 / kFusedThreads; ++k) {
+            const int i4 = tid + k * kFusedThreads;
+            const float* d = &xs[i4 >> 4][(i4 & 15) << 2];
+            reinterpret_cast<float4*>(yr + n_base)[i4] = make_float4(d[0], d[1], d[2], d[3]);
+        }
+    } else {
+        for (int i = tid; i < kSeg; i += kFusedThreads) {
+            const int n = n_base + i;
+            const int idx = n - start;
+            if (idx >= 0 && idx < f.n_out && n < a.N) yr[idx] = xs[i / kSub][i % kSub];
+        }
+    }
+}
+
 int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -439,18 +799,25 @@ using namespace modfx;
 extern "C" int64_t modfx_phaser_workspace_bytes(int32_t B, int64_t N) {
     if (B <= 0 || N <= 0) return 0;
     const int64_t n_ctl = (N + kUpd - 1) / kUpd, n_chunks = (N + kChunk - 1) / kChunk;
-    return align_up((int64_t)B * n_ctl * 4, 256) + align_up((int64_t)B * n_chunks * kMapFloats * 4, 256) +
-           align_up((int64_t)B * n_chunks * kSFloats * 4, 256) +
-           align_up((int64_t)B * ((n_chunks + 31) / 32) * kMapFloats * 4, 256) +
-           align_up((int64_t)B * ((n_chunks + 31) / 32) * kSFloats * 4, 256);
+    const int64_t multi = align_up((int64_t)B * n_ctl * 4, 256) + align_up((int64_t)B * n_chunks * kMapFloats * 4, 256) +
+                          align_up((int64_t)B * n_chunks * kSFloats * 4, 256) +
+                          align_up((int64_t)B * ((n_chunks + 31) / 32) * kMapFloats * 4, 256) +
+                          align_up((int64_t)B * ((n_chunks + 31) / 32) * kSFloats * 4, 256);
+    const int64_t n_seg = (N + kSeg - 1) / kSeg;
+    const int64_t fused = 256 + align_up((int64_t)B * n_seg * 4, 256) + align_up((int64_t)B * n_seg * kRec * 4, 256) +
+                          align_up((int64_t)B * n_chunks * 8, 256);
+    return (multi > fused ? multi : fused) + 256;
 }
 
-extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, const float* rate_hz,
-                                const float* depth, const float* centre_hz, const float* feedback,
-                                const float* mix, int32_t block, const int32_t* example_index, int32_t n_items,
-                                void* workspace, void* stream) {
+namespace {
+
+int phaser_launch(const float* x, float* y, float* dry_out, int32_t B, int64_t N, int64_t n_out, const int32_t* start,
+                  float sr, const float* rate_hz, const float* depth, const float* centre_hz, const float* feedback,
+                  const float* mix, int32_t block, const int32_t* example_index, int32_t n_items, void* workspace,
+                  void* stream) {
     MODFX_REQUIRE(x && y && rate_hz && depth && centre_hz && feedback && mix, "NULL pointer");
     MODFX_REQUIRE(B >= 0 && N >= 1 && N < (1ll << 30), "bad shape B=%d N=%lld", B, (long long)N);
+    MODFX_REQUIRE(n_out >= 1 && n_out <= N, "bad output window n_out=%lld (row length %lld)", (long long)n_out, (long long)N);
     MODFX_REQUIRE(sr > 0.0f, "sample rate must be positive");
     if (block <= 0) block = 8192;           // pedalboard's default buffer_size
     PhaserArgs a{};
@@ -463,16 +830,43 @@ extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, 
     MODFX_REQUIRE(a.n_items > 0 && workspace, "workspace is NULL or n_items=%d", a.n_items);
     a.n_ctl = (int)((N + kUpd - 1) / kUpd);
     a.n_chunks = (int)((N + kChunk - 1) / kChunk);
+    cudaStream_t s = as_stream(stream);
     char* w = static_cast<char*>(workspace);
+    const int n_blocks = (int)((N + block - 1) / block);
+
+    const char* force = getenv("MODFX_PHASER_KERNEL");
+    const bool fused_ok = (block % kChunk == 0) && !(force && force[0] == 'm');
+    if (fused_ok) {
+        // ---- single-pass fused kernel
+        FusedArgs f{};
+        f.a = a;
+        f.start = start; f.n_out = (int)n_out; f.dry_out = dry_out;
+        f.n_seg = (int)((N + kSeg - 1) / kSeg);
+        f.ticket = reinterpret_cast<int*>(w);                                     w += 256;
+        f.flags = reinterpret_cast<int*>(w);
+        const int64_t flag_bytes = align_up((int64_t)a.n_items * f.n_seg * 4, 256);  w += flag_bytes;
+        f.rec = reinterpret_cast<float*>(w);                                      w += align_up((int64_t)a.n_items * f.n_seg * kRec * 4, 256);
+        f.ph = reinterpret_cast<float2*>(w);
+        MODFX_CUDA_OK(cudaMemsetAsync(workspace, 0, (size_t)(256 + flag_bytes), s));
+        const int pairs = a.n_items * n_blocks;
+        phaser_phase_kernel<<<(pairs + 127) / 128, 128, 0, s>>>(f, n_blocks);
+        const size_t smem = sizeof(float) * (size_t)(kSubs * (kSub + 1) + kSubs * (kSubCtl + 1) + kSubs * (kMapFloats + 1) + kSubs * kSFloats +
+                                                     8 * (kMapFloats + 1) + 8 * kSFloats);
+        const int64_t tiles = (int64_t)a.n_items * f.n_seg;
+        MODFX_REQUIRE(tiles < (1ll << 31), "too many segments in one call");
+        phaser_fused_kernel<<<(unsigned)tiles, kFusedThreads, smem, s>>>(f);
+        MODFX_CUDA_OK(cudaGetLastError());
+        return MODFX_OK;
+    }
+    // ---- four-kernel pipeline (host blocks that are not a multiple of 128 samples; MODFX_PHASER_KERNEL=multi)
+    if (start || dry_out || n_out != N)
+        return fail(MODFX_ERR_UNSUPPORTED, "cropped output needs a host block size that is a multiple of %d samples", kChunk);
     a.C = reinterpret_cast<float*>(w);
     w += align_up((int64_t)a.n_items * a.n_ctl * 4, 256);
     a.Mw = reinterpret_cast<float*>(w);
     w += align_up((int64_t)a.n_items * a.n_chunks * kMapFloats * 4, 256);
     a.S = reinterpret_cast<float*>(w);
     w += align_up((int64_t)a.n_items * a.n_chunks * kSFloats * 4, 256);
-    cudaStream_t s = as_stream(stream);
-
-    const int n_blocks = (int)((N + block - 1) / block);
     {
         const int total = a.n_items * n_blocks;
         phaser_ctl_kernel<<<(total + 31) / 32, kK0Threads, 0, s>>>(a, n_blocks);
@@ -503,4 +897,23 @@ extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, 
     }
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
+}
+
+}  // namespace
+
+extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, float sr, const float* rate_hz,
+                                const float* depth, const float* centre_hz, const float* feedback,
+                                const float* mix, int32_t block, const int32_t* example_index, int32_t n_items,
+                                void* workspace, void* stream) {
+    return phaser_launch(x, y, nullptr, B, N, N, nullptr, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
+                         n_items, workspace, stream);
+}
+
+extern "C" int modfx_phaser_crop_f32(const float* x, float* y, float* dry_out, int32_t B, int64_t N, int64_t n_out,
+                                     const int32_t* start, float sr, const float* rate_hz, const float* depth,
+                                     const float* centre_hz, const float* feedback, const float* mix, int32_t block,
+                                     const int32_t* example_index, int32_t n_items, void* workspace, void* stream) {
+    MODFX_REQUIRE(start, "start is NULL");
+    return phaser_launch(x, y, dry_out, B, N, n_out, start, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
+                         n_items, workspace, stream);
 }

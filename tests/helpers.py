@@ -46,7 +46,7 @@ def snr_db(ref, got):
 #    3.5e-3 (tonal rows) away from the same transform with a float64 FFT, because a band 80-100 dB below the frame's
 #    peak carries the float32 rounding noise of the whole FFT.  The bar is therefore stated relative to the reference:
 #    (a) the kernel must be at least as close to exact (float64-FFT) arithmetic as the reference is, on the extreme
-#        element (25 % slack: the maximum of ~1e5 noise samples is itself noisy) and at the 99.99th percentile;
+#        element (factor 2: the maximum of ~1e5 noise samples is itself noisy) and, within 25 %, at the 99.99th percentile;
 #    (b) the distance kernel <-> reference is bounded by the measured one with <= 2x head-room, per audio family.
 #        (measured: profiles/r02_parity_logmel.txt; the inputs are fixed, so these are not statistical bounds)
 _REF_BOUND = {"white_2ch_22050": 2.5e-4, "guitar_2ch_22050": 1.3e-3, "white_1ch_88200": 3e-5, "silence_and_click": 4e-6,
@@ -77,8 +77,11 @@ def check_logmel_case(name, y, ref, tru):
     e_rt = np.abs(ref.astype(np.float64) - tru)
     assert snr_db(ref, y) >= 80.0, (name, snr_db(ref, y))
     assert snr_db(tru, y) >= 80.0, (name, snr_db(tru, y))
-    # (errors below half the stated 1e-4 tolerance need no comparison: both sides are inside the bar there)
-    assert e_gt.max() <= max(1.25 * e_rt.max(), 5e-5), (name, "max vs float64", e_gt.max(), e_rt.max())
+    # (errors below half the stated 1e-4 tolerance need no comparison: both sides are inside the bar there; the maximum
+    # of ~1e5..1e6 heavy-tailed noise samples differs by up to ~1.6x between two equally accurate float32 FFTs -- measured
+    # 0.4x .. 1.6x over the cases of profiles/r02_parity_logmel.txt and the smoke rows -- hence the factor 2 on the
+    # extreme element and the tight factor on the 99.99th percentile below)
+    assert e_gt.max() <= max(2.0 * e_rt.max(), 5e-5), (name, "max vs float64", e_gt.max(), e_rt.max())
     assert np.quantile(e_gt, 0.9999) <= 1.25 * np.quantile(e_rt, 0.9999) + _LOG_ULP_FLOOR / 2, \
         (name, "p99.99 vs float64", np.quantile(e_gt, 0.9999), np.quantile(e_rt, 0.9999))
     if name in _REF_BOUND:
