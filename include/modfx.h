@@ -123,6 +123,15 @@ int modfx_tremolo_f32(const float* x, float* y, int32_t B, int32_t C, int64_t N,
 int modfx_lfo_f32(float* out, int32_t B, int64_t n, float sr, const float* freq, const float* phase,
                   const int32_t* shape, const float* exp_or_null, void* stream);
 
+/*
+ * Ground-truth LFO of PedalboardPhaserDataset.__getitem__, mod_extraction/datasets.py:442-450, without materialising
+ * the audio-rate signal: out (B, n_out) = linear_interpolate_last_dim(make_mod_signal(..)[start[b] : start[b] + n_window],
+ * n_out, align_corners=True).  freq / phase already halved for rect shapes; start may be NULL (0).
+ */
+int modfx_lfo_window_f32(float* out, int32_t B, int64_t n_out, int64_t n_window, float sr, const float* freq,
+                         const float* phase, const int32_t* shape, const float* exp_or_null,
+                         const int32_t* start_or_null, void* stream);
+
 /* Replaces util.linear_interpolate_last_dim, mod_extraction/util.py:15-29 (F.interpolate
  * mode="linear").  in (rows, I) -> out (rows, O). */
 int modfx_interp_linear_f32(const float* in, float* out, int64_t rows, int64_t I, int64_t O,

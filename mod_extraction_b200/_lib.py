@@ -63,6 +63,7 @@ _SIGNATURES = {
                                          ctypes.c_int),
     "modfx_tremolo_f32": ([_vp, _vp, _i32, _i32, _i64, ctypes.POINTER(ModfxModSource), ModfxParam, _vp], ctypes.c_int),
     "modfx_lfo_f32": ([_vp, _i32, _i64, ctypes.c_float, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "modfx_lfo_window_f32": ([_vp, _i32, _i64, _i64, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "modfx_interp_linear_f32": ([_vp, _vp, _i64, _i64, _i64, _i32, _vp], ctypes.c_int),
     "modfx_find_corners_f32": ([_vp, _vp, _vp, _i64, _i64, _vp], ctypes.c_int),
     "modfx_lfo_sections_f32": ([_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),

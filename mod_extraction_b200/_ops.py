@@ -168,6 +168,25 @@ def lfo(n: int, sr: float, freq: Tensor, phase: Tensor, shape: Tensor, exp: Opti
     return out
 
 
+def lfo_window(n_out: int, n_window: int, sr: float, freq: Tensor, phase: Tensor, shape: Tensor,
+               start: Optional[Tensor] = None, exp: Optional[Tensor] = None) -> Tensor:
+    """(B, n_out) = linear_interpolate_last_dim(make_mod_signal(...)[start : start + n_window], n_out) per example
+    (datasets.py:442-450), computed from the LFO's closed form."""
+    _require_cuda(freq, "freq")
+    B, dev = freq.numel(), freq.device
+    out = torch.empty((B, n_out), device=dev, dtype=torch.float32)
+    keep = _Keep()
+    with torch.cuda.device(dev):
+        f = keep(freq.contiguous())
+        p = keep(phase.to(device=dev, dtype=torch.float32).contiguous())
+        s = keep(shape.to(device=dev, dtype=torch.int32).contiguous())
+        e = None if exp is None else keep(exp.to(device=dev, dtype=torch.float32).contiguous())
+        st = None if start is None else keep(start.to(device=dev, dtype=torch.int32).contiguous())
+        _lib.check(_lib.lib().modfx_lfo_window_f32(_ptr(out), B, n_out, n_window, float(sr), _ptr(f), _ptr(p), _ptr(s),
+                                                   _ptr(e), _ptr(st), _stream()))
+    return out
+
+
 def interp_linear(x: Tensor, n: int, align_corners: bool = True) -> Tensor:
     _require_cuda(x, "x")
     x = x.contiguous()

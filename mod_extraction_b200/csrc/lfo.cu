@@ -346,3 +346,51 @@ extern "C" int modfx_combined_lfo_f32(float* out, int32_t B, int64_t n, float sr
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Ground-truth LFO of PedalboardPhaserDataset.__getitem__ (datasets.py:442-450) without the audio-rate signal:
+//   mod = make_mod_signal(proc_n, sr, rate, phase, shape)[start : start + n_window]      (datasets.py:442, 448)
+//   out = linear_interpolate_last_dim(mod, n_out, align_corners=True)                    (datasets.py:450)
+// Element i of out only needs the two LFO values around scale * i inside the window, and make_mod_signal has a closed
+// form per element (lfo_value), so each output is two evaluations and the blend of util.py:15-29.
+namespace modfx {
+namespace {
+__global__ void __launch_bounds__(256) lfo_window_kernel(float* __restrict__ out, int n_out, int n_window, float sr,
+                                                         const float* __restrict__ freq, const float* __restrict__ phase,
+                                                         const int32_t* __restrict__ shape, const float* __restrict__ exp_,
+                                                         const int32_t* __restrict__ start) {
+    const int b = blockIdx.y;
+    const LfoDesc d = make_lfo_desc(freq[b], phase[b], shape[b], exp_ ? exp_[b] : 1.0f, sr);
+    const int s0 = start ? start[b] : 0;
+    const float scale = upsample_scale_ac_dev(n_window, n_out);
+    float* o = out + (int64_t)b * n_out;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) {
+        if (n_out == n_window) {                            // util.py:18-19: same length => untouched
+            o[i] = lfo_value(d, s0 + i);
+            continue;
+        }
+        const float src = __fmul_rn(scale, (float)i);
+        int i0 = min((int)src, n_window - 1);
+        const int i1 = i0 + ((i0 < n_window - 1) ? 1 : 0);
+        const float l1 = __fsub_rn(src, (float)i0);
+        const float l0 = __fsub_rn(1.0f, l1);
+        o[i] = __fmaf_rn(l0, lfo_value(d, s0 + i0), __fmul_rn(l1, lfo_value(d, s0 + i1)));
+    }
+}
+}  // namespace
+}  // namespace modfx
+
+extern "C" int modfx_lfo_window_f32(float* out, int32_t B, int64_t n_out, int64_t n_window, float sr, const float* freq,
+                                    const float* phase, const int32_t* shape, const float* exp_or_null,
+                                    const int32_t* start_or_null, void* stream) {
+    MODFX_REQUIRE(out && freq && phase && shape, "NULL pointer");
+    MODFX_REQUIRE(B >= 0 && n_out >= 1 && n_window >= 1 && n_window < (1ll << 30) && n_out <= n_window && sr > 0.0f,
+                  "bad arguments B=%d n_out=%lld n_window=%lld", B, (long long)n_out, (long long)n_window);
+    if (B == 0) return MODFX_OK;
+    MODFX_REQUIRE(B <= 65535, "B=%d exceeds grid.y", B);
+    const int gx = (int)std::min<int64_t>((n_out + 255) / 256, 256);
+    lfo_window_kernel<<<dim3(gx, B), 256, 0, as_stream(stream)>>>(out, (int)n_out, (int)n_window, sr, freq, phase, shape,
+                                                                  exp_or_null, start_or_null);
+    MODFX_CUDA_OK(cudaGetLastError());
+    return MODFX_OK;
+}

@@ -82,3 +82,52 @@ def test_apply_pedalboard_phaser_draw_order():
     assert p == {"depth": depth, "feedback": feedback, "mix": mix, "rate_hz": 1.7, "shape": "cos"}
     ref = oracle.phaser(x.numpy(), 44100.0, 1.7, depth, centre, feedback, mix)
     assert np.abs(y.numpy() - ref).max() <= 1e-4
+
+
+def test_phaser_render_step_follows_getitem_example_by_example():
+    """Batched PedalboardPhaserDataset.__getitem__ (datasets.py:428-453): per-example draw order on both RNG streams,
+    one extra LFO period rendered, random crop of dry / wet, ground-truth LFO cropped and resampled to n // 100 points.
+    The restatement below walks the examples with the reference's scalar draws; the DSP is this repo's own phaser
+    restatement (PARITY UNPINNED)."""
+    from scipy.stats import loguniform
+    from mod_extraction_b200.phaser import PhaserRenderStep
+    cfg = {"pedalboard_phaser": {"rate_hz": {"min": 0.5, "max": 3.0}, "depth": {"min": 0.2, "max": 1.0},
+                                 "centre_frequency_hz": {"min": 70.0, "max": 18000.0},
+                                 "feedback": {"min": 0.0, "max": 0.7}, "mix": {"min": 0.2, "max": 1.0}}}
+    sr, n, B = 44100.0, 22050, 7
+    step = PhaserRenderStep(cfg, n, sr)
+    L = step.max_proc_n_samples
+    assert L == n + 88200
+    audio = white((B, 1, L), 31)
+    torch.manual_seed(12)
+    np.random.seed(12)
+    dry, wet, mod_sig, fx = step(torch.from_numpy(audio).to(DEV))
+    tail_t, tail_n = torch.rand(2), np.random.uniform(size=2)
+    assert dry.shape == (B, 1, n) and wet.shape == (B, 1, n) and mod_sig.shape == (B, n // 100)
+    torch.manual_seed(12)
+    np.random.seed(12)
+    c = cfg["pedalboard_phaser"]
+    for b in range(B):
+        rate = float(loguniform.rvs(c["rate_hz"]["min"], c["rate_hz"]["max"], size=1)[0])          # datasets.py:429-432
+        proc_n = n + int((sr / rate) + 0.5)
+        chunk = audio[b, :, :proc_n]
+        depth = (torch.rand(1) * (c["depth"]["max"] - c["depth"]["min"]) + c["depth"]["min"]).item()
+        centre = float(loguniform.rvs(c["centre_frequency_hz"]["min"], c["centre_frequency_hz"]["max"], size=1)[0])
+        feedback = (torch.rand(1) * (c["feedback"]["max"] - c["feedback"]["min"]) + c["feedback"]["min"]).item()
+        mix = (torch.rand(1) * (c["mix"]["max"] - c["mix"]["min"]) + c["mix"]["min"]).item()
+        proc = oracle.phaser(chunk, sr, rate, depth, centre, feedback, mix)
+        gt = oracle.make_mod_signal(proc_n, sr, rate, np.pi / 2, "cos")                              # datasets.py:442
+        start = torch.randint(low=0, high=proc_n - n + 1, size=(1,)).item()                         # datasets.py:445
+        assert fx["rate_hz"][b].item() == rate and fx["depth"][b].item() == depth
+        assert fx["feedback"][b].item() == feedback and fx["mix"][b].item() == mix and fx["shape"][b] == "cos"
+        assert np.array_equal(dry[b].cpu().numpy(), chunk[:, start:start + n])
+        assert np.abs(wet[b].cpu().numpy() - proc[:, start:start + n]).max() <= 1e-4
+        ref_mod = oracle.linear_interpolate_last_dim(gt[None, start:start + n], n // 100)[0]       # datasets.py:448-450
+        # 60-second-deep float32 LFO arguments: the reference's own closed form (SURVEY F3a), cos within 1 ulp
+        assert np.abs(mod_sig[b].cpu().numpy() - ref_mod).max() <= 1e-6
+    assert torch.equal(tail_t, torch.rand(2)) and np.array_equal(tail_n, np.random.uniform(size=2))
+    # CPU tensors in -> CPU tensors out, same numbers
+    torch.manual_seed(12)
+    np.random.seed(12)
+    d2, w2, m2, _ = step(torch.from_numpy(audio))
+    assert not w2.is_cuda and torch.equal(w2, wet.cpu()) and torch.equal(d2, dry.cpu()) and torch.equal(m2, mod_sig.cpu())
