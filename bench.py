@@ -82,6 +82,9 @@ def host_params(B, seed):
           "centre_frequency_hz": logU(70.0, 18000.0).astype(np.float32), "feedback": U(0.0, 0.7), "mix": U(0.2, 1.0)}
     lfo_rate = logU(1.0, 3.0)
     lfo_phase = rng.uniform(0.0, 2 * math.pi, B)
+    # phaser examples are rendered over one extra LFO period and cropped at a random start (datasets.py:433-447)
+    extra = (SR / ph["rate_hz"].astype(np.float64) + 0.5).astype(np.int64)
+    ph["start_idx"] = (rng.randint(0, 1 << 30, B) % (extra + 1)).astype(np.int32)
     return effect, fc, ph, lfo_rate, lfo_phase
 
 
@@ -169,7 +172,7 @@ def oracle_step(dry, effect, mod_lo, fc, ph, threads, fb=None):
                                              sr=SR, max_min_delay_ms=mmd, max_lfo_delay_ms=mld)
     idx = np.nonzero(effect == 2)[0]
     if idx.size:
-        wet[idx, 0] = oracle.phaser(dry[idx, 0], float(SR), *[ph[kk][idx] for kk in PH_KEYS])
+        wet[idx, 0] = oracle.phaser(dry[idx, 0], float(SR), *[ph[kk][idx] for kk in PH_KEYS])    # (no extra period here)
     both = np.concatenate([dry, wet], axis=1)                    # lightning.py:106
     return wet, _oracle_logmel_rows(both, threads, fb)
 
@@ -378,7 +381,7 @@ def roofline_block(kernels, dom, names, peak, peak_src, pipeline=None):
 KERNEL_NAMES = {"logmel": "logmel_kernel (one launch over B dry rows; the wet half is a second identical launch)",
                 "flanger": "fc_cta_kernel<control-rate> (flanger group, one CTA of 3 producer warps + 1 consumer warp per delay line)",
                 "chorus": "fc_wide_kernel (chorus group)",
-                "phaser": "phaser_{ctl,map,chain,run}_kernel"}
+                "phaser": "phaser_fused_kernel (+ phaser_phase_kernel), phaser rows rendered over N + one LFO period and cropped"}
 
 
 def bit_checksum(torch, t):
@@ -397,7 +400,7 @@ def run_config4(cx, args):
     from mod_extraction_b200.sharding import shard_range
     n_lo = N // 100
     nm = N_MELS * n_frames(N)
-    bytes_per_example = N * 4 + N * 4 + 2 * nm * 4                  # read dry, write wet, write log-mel = 1 412 160
+    L_PH = N + int(SR / 0.5 + 0.5)                                  # N + one period of the slowest phaser LFO (0.5 Hz)
     R = InterwovenRenderer(N, float(SR), dev)
 
     def make_batch(Bg, seed, lo, hi):
@@ -408,15 +411,24 @@ def run_config4(cx, args):
         mod_all = make_combined_mod_sig_batch(n_lo, SR // 100, rate, phase, SHAPES6, device=dev)
         torch.cuda.synchronize()
         lfo_s = time.perf_counter() - t0
+        # the longer chunks of this shard's phaser examples (N + one period of the slowest LFO, rows in batch order)
+        n_ph = int((effect[lo:hi] == 2).sum())
+        ph_before = int((effect[:lo] == 2).sum())
+        n_ph_all = int((effect == 2).sum())
         b = {"dry": cx.white(Bg, N, seed, lo, hi), "effect": torch.from_numpy(effect[lo:hi].copy()),
+             "ph_long": cx.white(n_ph_all, L_PH, seed + 7, ph_before, ph_before + n_ph).view(n_ph, L_PH),
+             "ph_start": torch.from_numpy(ph_np["start_idx"][lo:hi].copy()).to(dev),
+             "read_samples": int(np.where(effect[lo:hi] == 2, ph_np["start_idx"][lo:hi].astype(np.int64) + N, N).sum()),
              "mod_lo": mod_all[lo:hi].contiguous(), "rate": rate[lo:hi], "phase": phase[lo:hi],
              "fc": {k: torch.from_numpy(v[lo:hi].copy()).to(dev) for k, v in fc_np.items()},
-             "ph": {k: torch.from_numpy(v[lo:hi].copy()).to(dev) for k, v in ph_np.items()}, "lfo_s": lfo_s}
+             "ph": {k: torch.from_numpy(v[lo:hi].copy()).to(dev) for k, v in ph_np.items() if k != "start_idx"},
+             "lfo_s": lfo_s}
         b["wet"], b["logmel"] = R.alloc_outputs(hi - lo)
         return b
 
     def step_of(b):
-        return lambda: R.render(b["dry"], b["effect"], b["mod_lo"], b["fc"], b["ph"], wet=b["wet"], logmel=b["logmel"])
+        return lambda: R.render(b["dry"], b["effect"], b["mod_lo"], b["fc"], b["ph"], wet=b["wet"], logmel=b["logmel"],
+                                ph_long=b["ph_long"], ph_start=b["ph_start"])
 
     # ---------------- weak scaling: `value` (every rank its own batch, as in round 1)
     B = args.batch_per_gpu
@@ -427,6 +439,11 @@ def run_config4(cx, args):
     ms_per_step, clocks = cx.timed(step, args.steps, args.warmup, sampler)
     value = world * B * (N / SR) / (ms_per_step * 1e-3)
     checksum = float(wb["wet"].double().abs().mean().item())
+    # algorithmic bytes of the step: dry audio read once (a phaser example up to the end of its window: start + N
+    # samples of its longer chunk, plus the dry window written back), wet written, log-mel written
+    n_phx = int((wb["effect"] == 2).sum())
+    step_bytes = wb["read_samples"] * 4 + n_phx * N * 4 + B * N * 4 + B * 2 * nm * 4
+    bytes_per_example = step_bytes / B
 
     # ---------------- the same step with the LFO synthesis inside it (north_star puts it on the hot path)
     def step_with_lfo():
@@ -442,7 +459,7 @@ def run_config4(cx, args):
 
     # ---------------- per-kernel durations, serialised (same launches, one stream) for the roofline
     Rs = InterwovenRenderer(N, float(SR), dev, concurrent=False)
-    i_fl, i_ch, i_ph, _ = Rs._groups(wb["effect"])
+    i_fl, i_ch, i_ph, i_fc = Rs._groups(wb["effect"])
     fc_args = [wb["fc"][k] for k in FC_KEYS]
     ph_args = [wb["ph"][k] for k in PH_KEYS]
     dry, wet, logmel, mod_lo = wb["dry"], wb["wet"], wb["logmel"], wb["mod_lo"]
@@ -452,8 +469,9 @@ def run_config4(cx, args):
                                                 example_index=i_fl, out=wet), i_fl.numel() * N * 8, 1),
         "chorus": (lambda: _ops.flanger_chorus(dry, ModSource.control_rate(mod_lo), Rs.ch[0], Rs.ch[1], *fc_args,
                                                example_index=i_ch, out=wet), i_ch.numel() * N * 8, 2),
-        "phaser": (lambda: _ops.phaser(dry2, float(SR), *ph_args, example_index=i_ph, out=wet2),
-                   i_ph.numel() * N * 8, PHASER_LAUNCHES),
+        "phaser": (lambda: _ops.phaser_crop(wb["ph_long"], N, wb["ph_start"], float(SR), *ph_args, example_index=i_ph,
+                                            out=wet2, dry_out=dry2),
+                   (wb["read_samples"] - (B - n_phx) * N) * 4 + 2 * n_phx * N * 4, PHASER_LAUNCHES),
         "logmel": (lambda: Rs.front.forward_rows(dry2, N, B, logmel.view(-1), N, 2 * nm, None),
                    B * (N * 4 + nm * 4), 1),
     }
@@ -469,32 +487,37 @@ def run_config4(cx, args):
         t = traffic_tab.get(name, {}).get(key)
         kernels[name]["dram_traffic_bytes"] = None if t is None else t * n_units
     dom = max(kernels, key=lambda k: kernels[k]["ms"] * (2 if k == "logmel" else 1))
-    gbs_pipe = B * bytes_per_example / (ms_per_step * 1e-3) / 1e9
+    gbs_pipe = step_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = roofline_block(kernels, dom, KERNEL_NAMES, peak, peak_src,
-                              {"achieved": gbs_pipe, "frac": gbs_pipe / peak, "bytes_per_example": bytes_per_example})
+                              {"achieved": gbs_pipe, "frac": gbs_pipe / peak, "bytes_per_example": bytes_per_example,
+                               "bytes_per_step": step_bytes})
 
     # ---------------- end to end through the public API with host buffers (`e2e`), LFO synthesis included
     e2e = e2e_full = None
     if not args.no_e2e:
         pin = lambda t: t.cpu().pin_memory()
-        dry_h = torch.empty((B, 1, N), dtype=torch.float32).pin_memory()
-        dry_h.copy_(dry.cpu())
+        dry_h = torch.empty((B, 1, N), dtype=torch.float32, device="meta")        # shape only: see dry_fc_h
+        dry_fc_h = pin(dry.view(B, N).index_select(0, i_fc))                        # dry audio of the flanger / chorus examples
         fc_h = {k: pin(v) for k, v in wb["fc"].items()}
         ph_h = {k: pin(v) for k, v in wb["ph"].items()}
         wet_h = torch.empty((B, 1, N), dtype=torch.float32).pin_memory()
         stat_h = torch.empty((B, 2), dtype=torch.float32).pin_memory()
         dry_d = torch.empty_like(dry)
+        ph_long_h = pin(wb["ph_long"])
+        ph_start_h = pin(wb["ph_start"])
+        dry_ph_h = torch.empty((n_phx, N), dtype=torch.float32).pin_memory()
         words_bytes = B * 17 * 4 + 2 * B * 4                       # generator words + (rate, phase) of the LFO synthesis
-        h2d = dry_h.numel() * 4 + words_bytes + sum(v.numel() * 4 for v in fc_h.values()) + \
-            sum(v.numel() * 4 for v in ph_h.values())
-        d2h = wet_h.numel() * 4 + stat_h.numel() * 4 + 8
+        h2d = dry_fc_h.numel() * 4 + ph_long_h.numel() * 4 + ph_start_h.numel() * 4 + words_bytes + \
+            sum(v.numel() * 4 for v in fc_h.values()) + sum(v.numel() * 4 for v in ph_h.values())
+        d2h = wet_h.numel() * 4 + dry_ph_h.numel() * 4 + stat_h.numel() * 4 + 8
 
         def e2e_step(logmel_h=None):
             # host (rate, phase) + generator state in, pinned dry audio in; wet audio (+ log-mel) out to pinned host
             torch.manual_seed(43 + rank)
             m = make_combined_mod_sig_batch(n_lo, SR // 100, wb["rate"], wb["phase"], SHAPES6, device=dev)
             R.render_host(dry_h, wb["effect"], m, fc_h, ph_h, wet_h, logmel, stat_h, chunk=args.e2e_chunk,
-                          dry_d=dry_d, wet_d=wet, logmel_h=logmel_h)
+                          dry_d=dry_d, wet_d=wet, logmel_h=logmel_h, ph_long_h=ph_long_h, ph_start_h=ph_start_h,
+                          dry_ph_h=dry_ph_h, dry_fc_h=dry_fc_h)
 
         def host_timed(fn, n_rep):
             for _ in range(2):
@@ -511,7 +534,9 @@ def run_config4(cx, args):
         e2e = {"value": world * B * (N / SR) / dt, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": n_e2e, "chunk": args.e2e_chunk,
                "note": "per step: LFO synthesis from host (rate, phase) + generator words, then InterwovenRenderer.render_host: "
-                       "pinned host dry audio + parameters in, wet audio + per-example log-mel mean out, chunks pipelined over "
+                       "pinned host dry audio of the flanger / chorus examples + the longer chunks of the phaser examples + "
+                       "parameters in, wet audio + the dry "
+                       "windows of the phaser examples + per-example log-mel mean out, chunks pipelined over "
                        "copy/compute/copy streams; the (B,2,256,345) log-mel tensor stays in HBM where the extractor consumes "
                        "it (e2e_full delivers it to the host too)"}
         if not args.no_e2e_full:
@@ -582,7 +607,7 @@ def run_config4(cx, args):
     return line
 
 
-PHASER_LAUNCHES = 4
+PHASER_LAUNCHES = 3     # memset of the look-back flags, phase kernel, fused kernel
 
 
 # --------------------------------------------------------------------------------------------- configs 1, 2, 3, 5
@@ -632,18 +657,32 @@ def run_small_configs(cx, args):
                "note": "the reference's call site: CPU tensors in, CPU tensor out through MonoFlangerChorusModule "
                        "(H2D + kernel + D2H + sync per call)"}
     elif cfg == 2:
-        rate, depth, fcen, fb, mix = LU(0.5, 3), U(0.2, 1), LU(70, 18000), U(0, 0.7), U(0.2, 1)
-        ph = Phaser(SR)
-        prm = [dv(a) for a in (rate, depth, fcen, fb, mix)]
-        x2, o2 = x.view(B, n), out.view(B, n)
-        rate_h = rate[lo:hi].astype(np.float64)
+        # the online phaser of train_lfo_phaser: one batch of PedalboardPhaserDataset.__getitem__ (datasets.py:428-453):
+        # chunks of N + one LFO period, phaser from the first sample, random window of N, ground-truth LFO
+        from mod_extraction_b200.phaser import PhaserRenderStep
+        pcfg = {"rate_hz": {"min": 0.5, "max": 3.0}, "depth": {"min": 0.2, "max": 1.0},
+                "centre_frequency_hz": {"min": 70.0, "max": 18000.0}, "feedback": {"min": 0.0, "max": 0.7},
+                "mix": {"min": 0.2, "max": 1.0}}                          # configs/train_lfo_phaser.yml:33-48
+        prs = PhaserRenderStep(pcfg, n, float(SR))
+        np.random.seed(43)
+        torch.manual_seed(43)
+        allp = prs.sample_params(Bg)
+        params = {k: v[lo:hi] for k, v in allp.items()}
+        audio = cx.white(Bg, prs.max_proc_n_samples, 42 + cfg, lo, hi)
+        del x, out
+        holder = {}
 
         def step():
-            ph(x2, *prm, out=o2)
-            # ground-truth LFO of datasets.py:442: audio-rate cosine at phase pi/2 (here at the clip length)
-            extra["gt"] = M.make_mod_signal_batch(n, float(SR), rate_h, np.full(B, math.pi / 2), ["cos"] * B)
-        audio_s, launches, step_bytes = Bg * n / SR, PHASER_LAUNCHES + 1, B * n * 12
-        dominant = ("phaser", lambda: ph(x2, *prm, out=o2), B * n * 8)
+            holder["out"] = prs(audio, params)
+        step()
+        out = holder["out"][1]
+        read = int((params["start_idx"] + n).sum())
+        audio_s, launches, step_bytes = Bg * n / SR, PHASER_LAUNCHES + 1, read * 4 + B * n * 8 + B * (n // 100) * 4
+        rate_d, start_d = holder["out"][3]["rate_hz"].float().to(dev), torch.from_numpy(params["start_idx"].astype(np.int32)).to(dev)
+        prm = [torch.from_numpy(params[k].astype(np.float32)).to(dev) for k in ("rate_hz", "depth", "centre_frequency_hz", "feedback", "mix")]
+        from mod_extraction_b200 import _ops
+        a2 = audio.view(B, -1)
+        dominant = ("phaser", lambda: _ops.phaser_crop(a2, n, start_d, float(SR), *prm), read * 4 + B * n * 8)
     elif cfg == 3:
         half = Bg // 2
         rates_q, ph_q = LU(0.5, 2.0)[:half], U(0, 2 * math.pi)[:half]
@@ -728,7 +767,6 @@ def run_small_configs(cx, args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * launches, "roofline": roofline,
         "wet_abs_mean": float(out.double().abs().mean().item()), **extra,
     }
-    line.pop("gt", None)
     return line
 
 

@@ -88,7 +88,7 @@ _SIGNATURES = {
     "modfx_phaser_workspace_bytes": ([_i32, _i64], _i64),
     "modfx_phaser_f32": ([_vp, _vp, _i32, _i64, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp],
                          ctypes.c_int),
-    "modfx_phaser_crop_f32": ([_vp, _vp, _vp, _i32, _i64, _i64, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
+    "modfx_phaser_crop_f32": ([_vp, _i32, _vp, _vp, _i32, _i64, _i64, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
                                _vp, _vp], ctypes.c_int),
 }
 

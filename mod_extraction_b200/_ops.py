@@ -235,27 +235,41 @@ def phaser(x: Tensor, sr: float, rate_hz: Tensor, depth: Tensor, centre_hz: Tens
 
 
 def phaser_crop(x: Tensor, n_out: int, start: Tensor, sr: float, rate_hz: Tensor, depth: Tensor, centre_hz: Tensor,
-                feedback: Tensor, mix: Tensor, block: int = 8192, want_dry: bool = True):
-    """x: (B, N) CUDA float32 rows of (at least) start[b] + n_out samples.  Returns (wet (B, n_out), dry (B, n_out) or None):
-    the phaser over each row from its first sample, delivered on the window [start[b], start[b] + n_out)
-    (PedalboardPhaserDataset.__getitem__, datasets.py:436-447)."""
+                feedback: Tensor, mix: Tensor, block: int = 8192, want_dry: bool = True,
+                example_index: Optional[Tensor] = None, out: Optional[Tensor] = None, dry_out: Optional[Tensor] = None):
+    """x: (rows, L) CUDA float32 rows of (at least) start + n_out samples.  Returns (wet (B, n_out), dry (B, n_out) or
+    None): the phaser over each row from its first sample, delivered on the window [start, start + n_out)
+    (PedalboardPhaserDataset.__getitem__, datasets.py:436-447).
+    Without `example_index`: rows = B examples.  With it: x is COMPACT -- row i belongs to example example_index[i] --
+    while start, the parameters and the (B, n_out) outputs `out` / `dry_out` stay indexed by the example id."""
     _require_cuda(x, "x")
     assert x.ndim == 2
     x = x.contiguous()
-    B, N = x.shape
-    y = torch.empty((B, n_out), device=x.device, dtype=torch.float32)
-    dry = torch.empty((B, n_out), device=x.device, dtype=torch.float32) if want_dry else None
+    rows, L_ = x.shape
     keep = _Keep()
     with torch.cuda.device(x.device):
         ps = [keep(torch.as_tensor(p).detach().to(device=x.device, dtype=torch.float32).reshape(-1).contiguous())
               for p in (rate_hz, depth, centre_hz, feedback, mix)]
+        B = ps[0].numel()
         assert all(t.shape == (B,) for t in ps)
         st = keep(torch.as_tensor(start).to(device=x.device, dtype=torch.int32).reshape(-1).contiguous())
         assert st.shape == (B,)
+        idx_ptr, n_items, compact = ctypes.c_void_p(0), 0, 0
+        if example_index is not None:
+            idx = keep(example_index.to(device=x.device, dtype=torch.int32).contiguous())
+            assert idx.numel() == rows
+            idx_ptr, n_items, compact = ctypes.c_void_p(idx.data_ptr()), idx.numel(), 1
+        else:
+            assert rows == B
+        y = torch.empty((B, n_out), device=x.device, dtype=torch.float32) if out is None else out
+        dry = dry_out if dry_out is not None else (torch.empty((B, n_out), device=x.device, dtype=torch.float32) if want_dry else None)
+        assert y.is_contiguous() and y.numel() == B * n_out and (dry is None or (dry.is_contiguous() and dry.numel() == B * n_out))
+        if example_index is not None and n_items == 0:
+            return y, dry
         L = _lib.lib()
-        ws = keep(torch.empty((max(1, int(L.modfx_phaser_workspace_bytes(B, N))),), device=x.device, dtype=torch.uint8))
-        _lib.check(L.modfx_phaser_crop_f32(_ptr(x), _ptr(y), _ptr(dry), B, N, n_out, _ptr(st), float(sr),
-                                           *[_ptr(t) for t in ps], int(block), ctypes.c_void_p(0), 0, _ptr(ws), _stream()))
+        ws = keep(torch.empty((max(1, int(L.modfx_phaser_workspace_bytes(max(rows, 1), L_))),), device=x.device, dtype=torch.uint8))
+        _lib.check(L.modfx_phaser_crop_f32(_ptr(x), compact, _ptr(y), _ptr(dry), B, L_, n_out, _ptr(st), float(sr),
+                                           *[_ptr(t) for t in ps], int(block), idx_ptr, n_items, _ptr(ws), _stream()))
         ws.record_stream(torch.cuda.current_stream(x.device))
     return y, dry
 

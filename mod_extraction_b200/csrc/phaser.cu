@@ -465,6 +465,7 @@ struct FusedArgs {
     const int32_t* start;       // (B,) first delivered sample of each row, or nullptr (0)
     int n_out;                  // delivered samples per row
     float* dry_out;             // (B, n_out) window of the dry input, or nullptr
+    int x_compact;              // 1: row `item` of x (a compact (n_items, N) array), 0: row b like every other array
     int n_seg;
     int* ticket;                // 1 int, zero at launch
     int* flags;                 // (n_items, n_seg), zero at launch
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(kFusedThreads) phaser_fused_kernel(const Fused
     const int need = min(a.N, start + f.n_out);
     const int n_base = seg * kSeg;
     if (n_base >= need) return;
-    const float* xr = a.x + (int64_t)b * a.N;
+    const float* xr = a.x + (int64_t)(f.x_compact ? item : b) * a.N;
 
     // ---- A: audio + oscillator phases
     const bool vec = ((reinterpret_cast<uintptr_t>(xr) & 15) == 0) && (n_base + kSeg <= a.N);
@@ -811,7 +812,7 @@ extern "C" int64_t modfx_phaser_workspace_bytes(int32_t B, int64_t N) {
 
 namespace {
 
-int phaser_launch(const float* x, float* y, float* dry_out, int32_t B, int64_t N, int64_t n_out, const int32_t* start,
+int phaser_launch(const float* x, int x_compact, float* y, float* dry_out, int32_t B, int64_t N, int64_t n_out, const int32_t* start,
                   float sr, const float* rate_hz, const float* depth, const float* centre_hz, const float* feedback,
                   const float* mix, int32_t block, const int32_t* example_index, int32_t n_items, void* workspace,
                   void* stream) {
@@ -840,7 +841,7 @@ int phaser_launch(const float* x, float* y, float* dry_out, int32_t B, int64_t N
         // ---- single-pass fused kernel
         FusedArgs f{};
         f.a = a;
-        f.start = start; f.n_out = (int)n_out; f.dry_out = dry_out;
+        f.start = start; f.n_out = (int)n_out; f.dry_out = dry_out; f.x_compact = x_compact;
         f.n_seg = (int)((N + kSeg - 1) / kSeg);
         f.ticket = reinterpret_cast<int*>(w);                                     w += 256;
         f.flags = reinterpret_cast<int*>(w);
@@ -859,7 +860,7 @@ int phaser_launch(const float* x, float* y, float* dry_out, int32_t B, int64_t N
         return MODFX_OK;
     }
     // ---- four-kernel pipeline (host blocks that are not a multiple of 128 samples; MODFX_PHASER_KERNEL=multi)
-    if (start || dry_out || n_out != N)
+    if (start || dry_out || n_out != N || x_compact)
         return fail(MODFX_ERR_UNSUPPORTED, "cropped output needs a host block size that is a multiple of %d samples", kChunk);
     a.C = reinterpret_cast<float*>(w);
     w += align_up((int64_t)a.n_items * a.n_ctl * 4, 256);
@@ -905,15 +906,16 @@ extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, 
                                 const float* depth, const float* centre_hz, const float* feedback,
                                 const float* mix, int32_t block, const int32_t* example_index, int32_t n_items,
                                 void* workspace, void* stream) {
-    return phaser_launch(x, y, nullptr, B, N, N, nullptr, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
+    return phaser_launch(x, 0, y, nullptr, B, N, N, nullptr, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
                          n_items, workspace, stream);
 }
 
-extern "C" int modfx_phaser_crop_f32(const float* x, float* y, float* dry_out, int32_t B, int64_t N, int64_t n_out,
-                                     const int32_t* start, float sr, const float* rate_hz, const float* depth,
+extern "C" int modfx_phaser_crop_f32(const float* x, int32_t x_compact, float* y, float* dry_out, int32_t B, int64_t N,
+                                     int64_t n_out, const int32_t* start, float sr, const float* rate_hz, const float* depth,
                                      const float* centre_hz, const float* feedback, const float* mix, int32_t block,
                                      const int32_t* example_index, int32_t n_items, void* workspace, void* stream) {
     MODFX_REQUIRE(start, "start is NULL");
-    return phaser_launch(x, y, dry_out, B, N, n_out, start, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
+    MODFX_REQUIRE(!x_compact || example_index, "x_compact needs an example_index list");
+    return phaser_launch(x, x_compact ? 1 : 0, y, dry_out, B, N, n_out, start, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
                          n_items, workspace, stream);
 }

@@ -65,10 +65,10 @@ class InterwovenRenderer:
         for k in (FLANGER, CHORUS, PHASER):
             idx = torch.nonzero(e == k).reshape(-1).to(torch.int32)
             groups.append(idx.to(self.device))
-        dry_rows = torch.arange(hi - lo, dtype=torch.int32, device=self.device)
+        not_phaser = torch.nonzero(e != PHASER).reshape(-1).to(self.device)        # int64: rows whose dry audio is given
         if len(self._idx_cache) > 64:
             self._idx_cache.clear()
-        self._idx_cache[key] = (*groups, dry_rows)
+        self._idx_cache[key] = (*groups, not_phaser)
         return self._idx_cache[key]
 
     def alloc_outputs(self, B: int) -> Tuple[Tensor, Tensor]:
@@ -81,12 +81,20 @@ class InterwovenRenderer:
     def render_host(self, dry_h: Tensor, effect: Tensor, mod_lo_h: Tensor, fc_h: Dict[str, Tensor],
                     ph_h: Dict[str, Tensor], wet_h: Tensor, logmel: Tensor, stat_h: Optional[Tensor] = None,
                     chunk: int = 512, dry_d: Optional[Tensor] = None, wet_d: Optional[Tensor] = None,
-                    logmel_h: Optional[Tensor] = None) -> None:
+                    logmel_h: Optional[Tensor] = None, ph_long_h: Optional[Tensor] = None,
+                    ph_start_h: Optional[Tensor] = None, dry_ph_h: Optional[Tensor] = None,
+                    dry_fc_h: Optional[Tensor] = None) -> None:
         """Host-buffer entry point: pinned host dry audio + parameters in, wet audio out to the pinned host
         tensor `wet_h`; the log-mel tensor stays on the GPU (`logmel`, (B,2,n_mels,n_frames)) where the
         extractor consumes it, and `stat_h` (B, 2) receives its per-example mean; with `logmel_h` (pinned, same
         shape) the log-mel tensor is delivered to the host as well.  `mod_lo_h` may already live on the device
-        (LFOs generated there).  The batch is cut into chunks so that the H2D copy of chunk i+1, the kernels of
+        (LFOs generated there).  `ph_long_h` (n_phaser, L) pinned + `ph_start_h` (B,) int32: the longer chunks of the
+        phaser examples and their window starts (see `render`); the dry windows cut out of them come back in
+        `dry_ph_h` (n_phaser, N) pinned, one row per phaser example in batch order (the rows of `dry_h` that belong to
+        phaser examples are then not read).  `dry_fc_h` (n_flanger + n_chorus, N) pinned: the dry audio of the other
+        examples as a compact array in batch order -- the per-effect layout the reference's three datasets produce --
+        in which case `dry_h` is not read at all (pass a (B, 1, N) meta / empty tensor for the shape) and the rows are
+        scattered into the interleaved batch on the device.  The batch is cut into chunks so that the H2D copy of chunk i+1, the kernels of
         chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex); the call returns when everything has
         landed."""
         B, _, N = dry_h.shape
@@ -117,9 +125,26 @@ class InterwovenRenderer:
                 size = short
             edges.append((lo, lo + size))
             lo += size
+        cropped = ph_long_h is not None
+        if cropped:
+            assert ph_start_h is not None
+            is_ph = (effect.detach().reshape(-1).cpu() == PHASER)
+            ph_before = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(is_ph.to(torch.int64), 0)]).tolist()
+        assert dry_fc_h is None or cropped, "dry_fc_h goes with ph_long_h"
         for lo, hi in edges:
             with torch.cuda.stream(s_in):
-                dry_d[lo:hi].copy_(dry_h[lo:hi], non_blocking=True)
+                if dry_fc_h is None:
+                    dry_d[lo:hi].copy_(dry_h[lo:hi], non_blocking=True)
+                else:
+                    f0, f1 = lo - ph_before[lo], hi - ph_before[hi]
+                    stage = dry_fc_h[f0:f1].to(self.device, non_blocking=True)
+                    dry_d[lo:hi].view(hi - lo, N).index_copy_(0, self._groups(effect, lo, hi)[3], stage)
+                    stage.record_stream(s_in)
+                pl = pst = None
+                if cropped:
+                    r0, r1 = ph_before[lo], ph_before[hi]
+                    pl = ph_long_h[r0:r1].to(self.device, non_blocking=True)
+                    pst = ph_start_h[lo:hi].to(self.device, non_blocking=True)
                 m = mod_lo_h[lo:hi] if mod_lo_h.is_cuda else mod_lo_h[lo:hi].to(self.device, non_blocking=True)
                 f = {k: fc_h[k][lo:hi].to(self.device, non_blocking=True) for k in fc_keys}
                 p = {k: ph_h[k][lo:hi].to(self.device, non_blocking=True) for k in ph_keys}
@@ -127,12 +152,17 @@ class InterwovenRenderer:
                 ev_in.record(s_in)
             s_run.wait_event(ev_in)
             with torch.cuda.stream(s_run):
-                self.render(dry_d[lo:hi], effect, m, f, p, wet=wet_d[lo:hi], logmel=logmel[lo:hi], _range=(lo, hi))
+                self.render(dry_d[lo:hi], effect, m, f, p, wet=wet_d[lo:hi], logmel=logmel[lo:hi], _range=(lo, hi),
+                            ph_long=pl, ph_start=pst)
                 st_d = logmel[lo:hi].mean(dim=(2, 3)) if stat_h is not None else None
+                dph = None
+                if cropped and dry_ph_h is not None and r1 > r0:
+                    dph = dry_d[lo:hi].view(hi - lo, N).index_select(0, self._groups(effect, lo, hi)[2].to(torch.int64))
                 ev_run = torch.cuda.Event()
                 ev_run.record(s_run)
-                for t in (m, *f.values(), *p.values()):
-                    t.record_stream(s_run)
+                for t in (m, *f.values(), *p.values(), pl, pst):
+                    if t is not None:
+                        t.record_stream(s_run)
             s_out.wait_event(ev_run)
             with torch.cuda.stream(s_out):
                 wet_h[lo:hi].copy_(wet_d[lo:hi], non_blocking=True)
@@ -141,6 +171,9 @@ class InterwovenRenderer:
                 if stat_h is not None:
                     stat_h[lo:hi].copy_(st_d, non_blocking=True)
                     st_d.record_stream(s_out)
+                if dph is not None:
+                    dry_ph_h[r0:r1].copy_(dph, non_blocking=True)
+                    dph.record_stream(s_out)
         for st in self._io_streams:
             ev = torch.cuda.Event()
             ev.record(st)
@@ -150,14 +183,22 @@ class InterwovenRenderer:
     @torch.no_grad()
     def render(self, dry: Tensor, effect: Tensor, mod_lo: Tensor, fc: Dict[str, Tensor], ph: Dict[str, Tensor],
                wet: Optional[Tensor] = None, logmel: Optional[Tensor] = None,
-               _range: Optional[Tuple[int, int]] = None) -> Tuple[Tensor, Tensor]:
+               _range: Optional[Tuple[int, int]] = None, ph_long: Optional[Tensor] = None,
+               ph_start: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         """dry (B,1,N) CUDA float32; effect (B,) ints in {0: flanger, 1: chorus, 2: phaser};
         mod_lo (B, n_lo) control-rate LFO of the flanger / chorus examples (rows of phaser examples are
         ignored); fc: feedback, min_delay_width, width, depth, mix as (B,) tensors (data_modules.py:421-445);
         ph: rate_hz, depth, centre_frequency_hz, feedback, mix as (B,) tensors (datasets.py:461-470).
-        Returns (wet (B,1,N), logmel (B,2,n_mels,n_frames))."""
+        Returns (wet (B,1,N), logmel (B,2,n_mels,n_frames)).
+
+        The reference renders a phaser example over ``N + round(sr / rate_hz)`` samples and keeps a random window of N
+        (PedalboardPhaserDataset.__getitem__, datasets.py:428-447).  ``ph_long`` (n_phaser, L) holds those longer chunks,
+        one row per phaser example in batch order, and ``ph_start`` (B,) the window starts: the phaser then runs over the
+        long rows and writes the window of its wet output into ``wet`` AND the same window of the dry chunk into the
+        phaser rows of ``dry`` (in place), before their log-mel is taken.  Without ``ph_long`` the phaser rows of ``dry``
+        are rendered as they are (no extra period)."""
         assert dry.is_cuda and dry.dtype == torch.float32 and dry.ndim == 3 and dry.size(1) == 1
-        dry = dry.contiguous()
+        assert dry.is_contiguous()
         B, _, N = dry.shape
         assert N == self.n_samples
         if wet is None or logmel is None:
@@ -171,6 +212,9 @@ class InterwovenRenderer:
         nm = self.front.n_mels * self.n_frames
         dry2, wet2 = dry.view(B, N), wet.view(B, N)
         lm_dry, lm_wet = logmel.view(-1), logmel.view(-1)[nm:]
+        cropped = ph_long is not None and i_ph.numel() > 0
+        if cropped:
+            assert ph_start is not None and ph_long.is_cuda and ph_long.shape[0] == i_ph.numel() and ph_start.numel() == B
 
         def effects_fl():
             _ops.flanger_chorus(dry, src, self.fl[0], self.fl[1], *fc_args, example_index=i_fl, out=wet)
@@ -179,7 +223,11 @@ class InterwovenRenderer:
             _ops.flanger_chorus(dry, src, self.ch[0], self.ch[1], *fc_args, example_index=i_ch, out=wet)
 
         def effects_ph():
-            _ops.phaser(dry2, self.sr, *ph_args, block=self.phaser_buffer_size, example_index=i_ph, out=wet2)
+            if cropped:
+                _ops.phaser_crop(ph_long, N, ph_start, self.sr, *ph_args, block=self.phaser_buffer_size,
+                                 example_index=i_ph, out=wet2, dry_out=dry2)
+            else:
+                _ops.phaser(dry2, self.sr, *ph_args, block=self.phaser_buffer_size, example_index=i_ph, out=wet2)
 
         def mel(x2, out_flat, rows):
             if rows is not None and rows.numel() == 0:
@@ -201,16 +249,22 @@ class InterwovenRenderer:
             with torch.cuda.stream(s):
                 fn()
                 mel(wet2, lm_wet, rows)                   # same stream: starts when its own effect has finished
+                if cropped and rows is i_ph:
+                    mel(dry2, lm_dry, rows)               # the dry window of the phaser rows exists only now
                 ev = torch.cuda.Event()
                 ev.record(s)
             cur.wait_event(ev)
         s_dry.wait_event(start)
         with torch.cuda.stream(s_dry):
-            mel(dry2, lm_dry, None)                       # needs no effect: background work for the whole step
+            if cropped:                                   # needs no effect: background work for the whole step
+                mel(dry2, lm_dry, i_fl)
+                mel(dry2, lm_dry, i_ch)
+            else:
+                mel(dry2, lm_dry, None)
             fin = torch.cuda.Event()
             fin.record(s_dry)
         cur.wait_event(fin)
-        for t in (dry, mod_lo, wet, logmel, *fc_args, *ph_args):
+        for t in (dry, mod_lo, wet, logmel, ph_long, ph_start, *fc_args, *ph_args):
             if isinstance(t, Tensor) and t.is_cuda:
                 for s in self._streams:
                     t.record_stream(s)

@@ -79,3 +79,80 @@ def test_render_host_pipelined_equals_device_render():
     assert torch.equal(wet_h, wet_ref.cpu())
     assert torch.equal(lm, lm_ref)
     assert torch.allclose(stat_h, lm_ref.mean(dim=(2, 3)).cpu(), atol=1e-5)
+
+
+def test_renderer_phaser_rows_from_long_chunks():
+    """datasets.py:428-447 inside the interleaved batch: the phaser examples are rendered over N + one LFO period and a
+    window of N samples of wet AND dry is kept; the other rows are untouched by it."""
+    from oracle import oracle
+    from mod_extraction_b200.models import LogMelSpectrogram
+    from mod_extraction_b200.render import InterwovenRenderer
+    dev = torch.device("cuda", 0)
+    B = 12
+    dry, effect, mod_lo, fc, ph = bench.oracle_inputs(B, seed=21)
+    rng = np.random.RandomState(3)
+    phx = np.nonzero(effect == 2)[0]
+    extra = (bench.SR / ph["rate_hz"] + 0.5).astype(np.int64)                         # datasets.py:433
+    L = bench.N + int(extra[phx].max())
+    long_rows = ((rng.random_sample((phx.size, L)) * 2 - 1) * 0.5).astype(np.float32)
+    start = np.zeros(B, dtype=np.int32)
+    start[phx] = [rng.randint(0, extra[b] + 1) for b in phx]                          # datasets.py:445
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    fcd, phd = {k: to(v) for k, v in fc.items()}, {k: to(v) for k, v in ph.items()}
+    outs = []
+    for concurrent in (True, False):
+        d = to(dry)
+        R = InterwovenRenderer(bench.N, float(bench.SR), dev, concurrent=concurrent)
+        w, lm = R.render(d, torch.from_numpy(effect), to(mod_lo), fcd, phd, ph_long=to(long_rows), ph_start=to(start))
+        torch.cuda.synchronize()
+        outs.append((d.cpu().numpy(), w.cpu().numpy(), lm.cpu().numpy()))
+    for a, b_ in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b_)
+    d, w, lm = outs[0]
+    fb = LogMelSpectrogram().fb.numpy()
+    for k, b in enumerate(phx):
+        proc_n = bench.N + int(extra[b])
+        ref = oracle.phaser(long_rows[k:k + 1, :proc_n], float(bench.SR), *[ph[n][b:b + 1] for n in bench.PH_KEYS])[0]
+        s0 = int(start[b])
+        assert np.array_equal(d[b, 0], long_rows[k, s0:s0 + bench.N])                 # dry window, in place
+        assert np.abs(w[b, 0] - ref[s0:s0 + bench.N]).max() <= 1e-4
+        tru = oracle.log_mel(np.stack([d[b, 0], w[b, 0]]), fb=fb, fft_dtype=np.float64)
+        assert (np.abs(lm[b] - tru) <= 1e-4).mean() >= 0.9999
+    others = np.nonzero(effect != 2)[0]
+    assert np.array_equal(d[others], dry[others])
+    plain_w, _ = InterwovenRenderer(bench.N, float(bench.SR), dev).render(to(dry), torch.from_numpy(effect), to(mod_lo), fcd, phd)
+    assert np.array_equal(w[others], plain_w.cpu().numpy()[others])
+
+
+def test_render_host_grouped_buffers_equal_device_render():
+    """Host-buffer entry point with the per-effect layout: compact dry rows of the flanger / chorus examples + the longer
+    chunks of the phaser examples in, wet audio + the dry windows of the phaser examples out == one device render."""
+    from mod_extraction_b200.render import InterwovenRenderer
+    dev = torch.device("cuda", 0)
+    B = 26
+    dry, effect, mod_lo, fc, ph = bench.oracle_inputs(B, seed=9)
+    rng = np.random.RandomState(4)
+    phx, fcx = np.nonzero(effect == 2)[0], np.nonzero(effect != 2)[0]
+    extra = (bench.SR / ph["rate_hz"] + 0.5).astype(np.int64)
+    L = bench.N + int(extra[phx].max())
+    long_rows = ((rng.random_sample((phx.size, L)) * 2 - 1) * 0.5).astype(np.float32)
+    start = np.zeros(B, dtype=np.int32)
+    start[phx] = [rng.randint(0, extra[b] + 1) for b in phx]
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    R = InterwovenRenderer(bench.N, float(bench.SR), dev)
+    eff = torch.from_numpy(effect)
+    d_ref = to(dry)
+    w_ref, lm_ref = R.render(d_ref, eff, to(mod_lo), {k: to(v) for k, v in fc.items()}, {k: to(v) for k, v in ph.items()},
+                             ph_long=to(long_rows), ph_start=to(start))
+    torch.cuda.synchronize()
+    wet_h = torch.empty((B, 1, bench.N)).pin_memory()
+    dry_ph_h = torch.empty((phx.size, bench.N)).pin_memory()
+    stat_h = torch.empty((B, 2)).pin_memory()
+    _, lm = R.alloc_outputs(B)
+    R.render_host(torch.empty((B, 1, bench.N), device="meta"), eff, pin(mod_lo), {k: pin(v) for k, v in fc.items()},
+                  {k: pin(v) for k, v in ph.items()}, wet_h, lm, stat_h, chunk=7, ph_long_h=pin(long_rows),
+                  ph_start_h=pin(start), dry_ph_h=dry_ph_h, dry_fc_h=pin(dry[fcx, 0]))
+    assert torch.equal(wet_h, w_ref.cpu()) and torch.equal(lm, lm_ref)
+    assert torch.equal(dry_ph_h, d_ref.cpu()[phx, 0])
+    assert torch.allclose(stat_h, lm_ref.mean(dim=(2, 3)).cpu(), atol=1e-5)
