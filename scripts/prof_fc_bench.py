@@ -13,7 +13,7 @@ dev = torch.device("cuda", 0)
 effect_np, fc_np, ph_np, rate, phase = bench.host_params(B, 43)
 torch.manual_seed(43)
 dry = (torch.rand((B, 1, bench.N), device=dev) * 2 - 1) * 0.5
-mod_lo = make_combined_mod_sig_batch(bench.N_LO, bench.SR // 100, rate, phase, bench.SHAPES6, device=dev)
+mod_lo = make_combined_mod_sig_batch(bench.N // 100, bench.SR // 100, rate, phase, bench.SHAPES6, device=dev)
 fc = [torch.from_numpy(fc_np[k]).to(dev) for k in ("feedback", "min_delay_width", "width", "depth", "mix")]
 R = InterwovenRenderer(bench.N, float(bench.SR), dev, concurrent=False)
 i_fl, i_ch, i_ph, _ = R._groups(torch.from_numpy(effect_np))
