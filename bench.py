@@ -391,6 +391,81 @@ def bit_checksum(torch, t):
 
 # --------------------------------------------------------------------------------------------- config 4
 
+def make_batch4(cx, R, Bg, seed, lo, hi):
+    """Rows [lo, hi) of the global batch of Bg examples drawn from `seed` (the same on every rank)."""
+    torch, dev = cx.torch, cx.dev
+    from mod_extraction_b200.modulations import make_combined_mod_sig_batch
+    n_lo, L_PH = N // 100, N + int(SR / 0.5 + 0.5)      # N + one period of the slowest phaser LFO (0.5 Hz)
+    effect, fc_np, ph_np, rate, phase = host_params(Bg, seed)
+    torch.manual_seed(seed)
+    t0 = time.perf_counter()
+    mod_all = make_combined_mod_sig_batch(n_lo, SR // 100, rate, phase, SHAPES6, device=dev)
+    torch.cuda.synchronize()
+    lfo_s = time.perf_counter() - t0
+    # the longer chunks of this shard's phaser examples (N + one period of the slowest LFO, rows in batch order)
+    n_ph = int((effect[lo:hi] == 2).sum())
+    ph_before = int((effect[:lo] == 2).sum())
+    n_ph_all = int((effect == 2).sum())
+    b = {"dry": cx.white(Bg, N, seed, lo, hi), "effect": torch.from_numpy(effect[lo:hi].copy()),
+         "ph_long": cx.white(n_ph_all, L_PH, seed + 7, ph_before, ph_before + n_ph).view(n_ph, L_PH),
+         "ph_start": torch.from_numpy(ph_np["start_idx"][lo:hi].copy()).to(dev),
+         "read_samples": int(np.where(effect[lo:hi] == 2, ph_np["start_idx"][lo:hi].astype(np.int64) + N, N).sum()),
+         "mod_lo": mod_all[lo:hi].contiguous(), "rate": rate[lo:hi], "phase": phase[lo:hi],
+         "fc": {k: torch.from_numpy(v[lo:hi].copy()).to(dev) for k, v in fc_np.items()},
+         "ph": {k: torch.from_numpy(v[lo:hi].copy()).to(dev) for k, v in ph_np.items() if k != "start_idx"},
+         "lfo_s": lfo_s}
+    b["wet"], b["logmel"] = R.alloc_outputs(hi - lo)
+    return b
+
+
+def make_e2e_step(cx, R, wb, chunk):
+    """The host-buffer step behind `e2e`: returns (step(logmel_h=None), {"h2d": bytes, "d2h": bytes}).
+    Pinned host buffers in the per-effect layout the reference's three datasets produce: the dry audio of the flanger /
+    chorus examples as one compact array, the longer chunks of the phaser examples as another, parameters; wet audio
+    (+ the dry windows of the phaser examples + per-example log-mel mean) come back into pinned host buffers."""
+    torch, dev, rank = cx.torch, cx.dev, cx.rank
+    from mod_extraction_b200.modulations import make_combined_mod_sig_batch
+    B = wb["dry"].size(0)
+    n_lo = N // 100
+    dry, wet, logmel = wb["dry"], wb["wet"], wb["logmel"]
+    i_fc = R._groups(wb["effect"])[3]
+    n_phx = int((wb["effect"] == 2).sum())
+    pin = lambda t: t.cpu().pin_memory()
+    dry_h = torch.empty((B, 1, N), dtype=torch.float32, device="meta")        # shape only: see dry_fc_h
+    dry_fc_h = pin(dry.view(B, N).index_select(0, i_fc))                        # dry audio of the flanger / chorus examples
+    fc_h = {k: pin(v) for k, v in wb["fc"].items()}
+    ph_h = {k: pin(v) for k, v in wb["ph"].items()}
+    wet_h = torch.empty((B, 1, N), dtype=torch.float32).pin_memory()
+    stat_h = torch.empty((B, 2), dtype=torch.float32).pin_memory()
+    dry_d = torch.empty_like(dry)
+    # the phaser chunks as a collate function would hand them over: variable-length rows back to back (16-byte aligned
+    # starts), each cut to the prefix that determines its window (start + N samples; the effect is causal)
+    ph_start_h = pin(wb["ph_start"])
+    rows = np.nonzero(wb["effect"].numpy() == 2)[0]
+    lens = (ph_start_h.numpy()[rows].astype(np.int64) + N + 3) // 4 * 4
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ph_packed_h = torch.empty((int(offs[-1]),), dtype=torch.float32).pin_memory()
+    ph_long_c = wb["ph_long"].cpu()
+    for i in range(n_phx):
+        ph_packed_h[offs[i]:offs[i + 1]] = ph_long_c[i, :lens[i]]
+    del ph_long_c
+    words_bytes = B * 17 * 4 + 2 * B * 4                       # generator words + (rate, phase) of the LFO synthesis
+    h2d = dry_fc_h.numel() * 4 + ph_packed_h.numel() * 4 + ph_start_h.numel() * 4 + n_phx * 8 + words_bytes + \
+        sum(v.numel() * 4 for v in fc_h.values()) + sum(v.numel() * 4 for v in ph_h.values())
+    d2h = wet_h.numel() * 4 + stat_h.numel() * 4 + 8
+
+    def lfos(blocking=False):
+        torch.manual_seed(43 + rank)
+        return make_combined_mod_sig_batch(n_lo, SR // 100, wb["rate"], wb["phase"], SHAPES6, device=dev, deferred=not blocking)
+
+    def e2e_step(logmel_h=None):
+        # host (rate, phase) + generator state in, pinned dry audio in; wet audio (+ log-mel) out to pinned host
+        R.render_host(dry_h, wb["effect"], lfos, fc_h, ph_h, wet_h, logmel, stat_h, chunk=chunk,
+                      dry_d=dry_d, wet_d=wet, logmel_h=logmel_h, ph_packed_h=ph_packed_h, ph_offsets=offs,
+                      ph_start_h=ph_start_h, dry_fc_h=dry_fc_h)
+    return e2e_step, {"h2d": h2d, "d2h": d2h}
+
+
 def run_config4(cx, args):
     torch, dev, rank, world = cx.torch, cx.dev, cx.rank, cx.world
     from mod_extraction_b200 import _ops
@@ -403,28 +478,7 @@ def run_config4(cx, args):
     L_PH = N + int(SR / 0.5 + 0.5)                                  # N + one period of the slowest phaser LFO (0.5 Hz)
     R = InterwovenRenderer(N, float(SR), dev)
 
-    def make_batch(Bg, seed, lo, hi):
-        """Rows [lo, hi) of the global batch of Bg examples drawn from `seed` (the same on every rank)."""
-        effect, fc_np, ph_np, rate, phase = host_params(Bg, seed)
-        torch.manual_seed(seed)
-        t0 = time.perf_counter()
-        mod_all = make_combined_mod_sig_batch(n_lo, SR // 100, rate, phase, SHAPES6, device=dev)
-        torch.cuda.synchronize()
-        lfo_s = time.perf_counter() - t0
-        # the longer chunks of this shard's phaser examples (N + one period of the slowest LFO, rows in batch order)
-        n_ph = int((effect[lo:hi] == 2).sum())
-        ph_before = int((effect[:lo] == 2).sum())
-        n_ph_all = int((effect == 2).sum())
-        b = {"dry": cx.white(Bg, N, seed, lo, hi), "effect": torch.from_numpy(effect[lo:hi].copy()),
-             "ph_long": cx.white(n_ph_all, L_PH, seed + 7, ph_before, ph_before + n_ph).view(n_ph, L_PH),
-             "ph_start": torch.from_numpy(ph_np["start_idx"][lo:hi].copy()).to(dev),
-             "read_samples": int(np.where(effect[lo:hi] == 2, ph_np["start_idx"][lo:hi].astype(np.int64) + N, N).sum()),
-             "mod_lo": mod_all[lo:hi].contiguous(), "rate": rate[lo:hi], "phase": phase[lo:hi],
-             "fc": {k: torch.from_numpy(v[lo:hi].copy()).to(dev) for k, v in fc_np.items()},
-             "ph": {k: torch.from_numpy(v[lo:hi].copy()).to(dev) for k, v in ph_np.items() if k != "start_idx"},
-             "lfo_s": lfo_s}
-        b["wet"], b["logmel"] = R.alloc_outputs(hi - lo)
-        return b
+    make_batch = lambda Bg, seed, lo, hi: make_batch4(cx, R, Bg, seed, lo, hi)
 
     def step_of(b):
         return lambda: R.render(b["dry"], b["effect"], b["mod_lo"], b["fc"], b["ph"], wet=b["wet"], logmel=b["logmel"],
@@ -495,29 +549,8 @@ def run_config4(cx, args):
     # ---------------- end to end through the public API with host buffers (`e2e`), LFO synthesis included
     e2e = e2e_full = None
     if not args.no_e2e:
-        pin = lambda t: t.cpu().pin_memory()
-        dry_h = torch.empty((B, 1, N), dtype=torch.float32, device="meta")        # shape only: see dry_fc_h
-        dry_fc_h = pin(dry.view(B, N).index_select(0, i_fc))                        # dry audio of the flanger / chorus examples
-        fc_h = {k: pin(v) for k, v in wb["fc"].items()}
-        ph_h = {k: pin(v) for k, v in wb["ph"].items()}
-        wet_h = torch.empty((B, 1, N), dtype=torch.float32).pin_memory()
-        stat_h = torch.empty((B, 2), dtype=torch.float32).pin_memory()
-        dry_d = torch.empty_like(dry)
-        ph_long_h = pin(wb["ph_long"])
-        ph_start_h = pin(wb["ph_start"])
-        dry_ph_h = torch.empty((n_phx, N), dtype=torch.float32).pin_memory()
-        words_bytes = B * 17 * 4 + 2 * B * 4                       # generator words + (rate, phase) of the LFO synthesis
-        h2d = dry_fc_h.numel() * 4 + ph_long_h.numel() * 4 + ph_start_h.numel() * 4 + words_bytes + \
-            sum(v.numel() * 4 for v in fc_h.values()) + sum(v.numel() * 4 for v in ph_h.values())
-        d2h = wet_h.numel() * 4 + dry_ph_h.numel() * 4 + stat_h.numel() * 4 + 8
-
-        def e2e_step(logmel_h=None):
-            # host (rate, phase) + generator state in, pinned dry audio in; wet audio (+ log-mel) out to pinned host
-            torch.manual_seed(43 + rank)
-            m = make_combined_mod_sig_batch(n_lo, SR // 100, wb["rate"], wb["phase"], SHAPES6, device=dev)
-            R.render_host(dry_h, wb["effect"], m, fc_h, ph_h, wet_h, logmel, stat_h, chunk=args.e2e_chunk,
-                          dry_d=dry_d, wet_d=wet, logmel_h=logmel_h, ph_long_h=ph_long_h, ph_start_h=ph_start_h,
-                          dry_ph_h=dry_ph_h, dry_fc_h=dry_fc_h)
+        e2e_step, io = make_e2e_step(cx, R, wb, args.e2e_chunk)
+        h2d, d2h = io["h2d"], io["d2h"]
 
         def host_timed(fn, n_rep):
             for _ in range(2):
@@ -533,10 +566,11 @@ def run_config4(cx, args):
         dt = host_timed(e2e_step, n_e2e)
         e2e = {"value": world * B * (N / SR) / dt, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": n_e2e, "chunk": args.e2e_chunk,
-               "note": "per step: LFO synthesis from host (rate, phase) + generator words, then InterwovenRenderer.render_host: "
-                       "pinned host dry audio of the flanger / chorus examples + the longer chunks of the phaser examples + "
-                       "parameters in, wet audio + the dry "
-                       "windows of the phaser examples + per-example log-mel mean out, chunks pipelined over "
+               "note": "per step, InterwovenRenderer.render_host: pinned host dry audio of the flanger / chorus examples + the "
+                       "variable-length chunks of the phaser examples (packed back to back, each cut to the start + N samples "
+                       "that determine its window) + parameters in, LFO synthesis on the device from host (rate, phase) + "
+                       "generator words behind the first copies, wet audio + per-example log-mel mean out (the dry windows of "
+                       "the phaser examples are slices of host data and are not copied back), chunks pipelined over "
                        "copy/compute/copy streams; the (B,2,256,345) log-mel tensor stays in HBM where the extractor consumes "
                        "it (e2e_full delivers it to the host too)"}
         if not args.no_e2e_full:

@@ -267,6 +267,19 @@ int modfx_phaser_crop_f32(const float* x, int32_t x_compact, float* y, float* dr
                           const int32_t* example_index, int32_t n_items, void* workspace, void* stream);
 
 /*
+ * The same step over a PACKED ragged input, the layout a collate function produces from the variable-length chunks
+ * PedalboardPhaserDataset reads (proc_n differs per example, mod_extraction/datasets.py:433-436): row i of x starts at
+ * x + x_offset[i] (float index, device array of n_items) and holds at least start[b] + n_out samples, b =
+ * example_index[i] -- the causal prefix that determines the delivered window; nothing past it is read.  N_max bounds
+ * start[b] + n_out over the call and sizes the workspace (modfx_phaser_workspace_bytes(n_items, N_max)).  Rows whose
+ * address is 16-byte aligned take the vector loads.
+ */
+int modfx_phaser_crop_packed_f32(const float* x, const int64_t* x_offset, float* y, float* dry_out, int32_t B, int64_t N_max,
+                                 int64_t n_out, const int32_t* start, float sr, const float* rate_hz, const float* depth,
+                                 const float* centre_hz, const float* feedback, const float* mix, int32_t block,
+                                 const int32_t* example_index, int32_t n_items, void* workspace, void* stream);
+
+/*
  * LFO-net body behind the log-mel front end: Spectral2DCNN.cnn, the mean over
  * mel bins, the 1x1 output convolution and the sigmoid, mod_extraction/models.py:183-195,209-214.
  * Activations between layers are channels-last float32: (B, H, W, C) with H = mel bins, W = frames.

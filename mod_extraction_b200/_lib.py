@@ -90,6 +90,8 @@ _SIGNATURES = {
                          ctypes.c_int),
     "modfx_phaser_crop_f32": ([_vp, _i32, _vp, _vp, _i32, _i64, _i64, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
                                _vp, _vp], ctypes.c_int),
+    "modfx_phaser_crop_packed_f32": ([_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
+                                      _i32, _vp, _vp], ctypes.c_int),
 }
 
 

@@ -236,16 +236,25 @@ def phaser(x: Tensor, sr: float, rate_hz: Tensor, depth: Tensor, centre_hz: Tens
 
 def phaser_crop(x: Tensor, n_out: int, start: Tensor, sr: float, rate_hz: Tensor, depth: Tensor, centre_hz: Tensor,
                 feedback: Tensor, mix: Tensor, block: int = 8192, want_dry: bool = True,
-                example_index: Optional[Tensor] = None, out: Optional[Tensor] = None, dry_out: Optional[Tensor] = None):
+                example_index: Optional[Tensor] = None, out: Optional[Tensor] = None, dry_out: Optional[Tensor] = None,
+                row_offsets: Optional[Tensor] = None, max_len: Optional[int] = None):
     """x: (rows, L) CUDA float32 rows of (at least) start + n_out samples.  Returns (wet (B, n_out), dry (B, n_out) or
     None): the phaser over each row from its first sample, delivered on the window [start, start + n_out)
     (PedalboardPhaserDataset.__getitem__, datasets.py:436-447).
     Without `example_index`: rows = B examples.  With it: x is COMPACT -- row i belongs to example example_index[i] --
-    while start, the parameters and the (B, n_out) outputs `out` / `dry_out` stay indexed by the example id."""
+    while start, the parameters and the (B, n_out) outputs `out` / `dry_out` stay indexed by the example id.
+    With `row_offsets` (int64, one per row of `example_index`) x is a PACKED 1-D array: row i starts at x[row_offsets[i]]
+    and holds start + n_out samples of example example_index[i]; `max_len` bounds start + n_out."""
     _require_cuda(x, "x")
-    assert x.ndim == 2
-    x = x.contiguous()
-    rows, L_ = x.shape
+    if row_offsets is not None:
+        assert x.ndim == 1 and example_index is not None and max_len is not None and max_len >= n_out
+        x = x.contiguous()
+        rows, L_ = example_index.numel(), int(max_len)
+        assert row_offsets.numel() == rows
+    else:
+        assert x.ndim == 2
+        x = x.contiguous()
+        rows, L_ = x.shape
     keep = _Keep()
     with torch.cuda.device(x.device):
         ps = [keep(torch.as_tensor(p).detach().to(device=x.device, dtype=torch.float32).reshape(-1).contiguous())
@@ -268,8 +277,13 @@ def phaser_crop(x: Tensor, n_out: int, start: Tensor, sr: float, rate_hz: Tensor
             return y, dry
         L = _lib.lib()
         ws = keep(torch.empty((max(1, int(L.modfx_phaser_workspace_bytes(max(rows, 1), L_))),), device=x.device, dtype=torch.uint8))
-        _lib.check(L.modfx_phaser_crop_f32(_ptr(x), compact, _ptr(y), _ptr(dry), B, L_, n_out, _ptr(st), float(sr),
-                                           *[_ptr(t) for t in ps], int(block), idx_ptr, n_items, _ptr(ws), _stream()))
+        if row_offsets is not None:
+            offs = keep(row_offsets.to(device=x.device, dtype=torch.int64).contiguous())
+            _lib.check(L.modfx_phaser_crop_packed_f32(_ptr(x), _ptr(offs), _ptr(y), _ptr(dry), B, L_, n_out, _ptr(st), float(sr),
+                                                      *[_ptr(t) for t in ps], int(block), idx_ptr, n_items, _ptr(ws), _stream()))
+        else:
+            _lib.check(L.modfx_phaser_crop_f32(_ptr(x), compact, _ptr(y), _ptr(dry), B, L_, n_out, _ptr(st), float(sr),
+                                               *[_ptr(t) for t in ps], int(block), idx_ptr, n_items, _ptr(ws), _stream()))
         ws.record_stream(torch.cuda.current_stream(x.device))
     return y, dry
 

@@ -466,6 +466,8 @@ struct FusedArgs {
     int n_out;                  // delivered samples per row
     float* dry_out;             // (B, n_out) window of the dry input, or nullptr
     int x_compact;              // 1: row `item` of x (a compact (n_items, N) array), 0: row b like every other array
+    const int64_t* x_offset;    // (n_items,) or nullptr: x is a packed ragged array, row `item` starts at x + x_offset[item]
+                                // and holds start + n_out samples (the prefix that determines the delivered window)
     int n_seg;
     int* ticket;                // 1 int, zero at launch
     int* flags;                 // (n_items, n_seg), zero at launch
@@ -551,10 +553,11 @@ __global__ void __launch_bounds__(kFusedThreads) phaser_fused_kernel(const Fused
     const int need = min(a.N, start + f.n_out);
     const int n_base = seg * kSeg;
     if (n_base >= need) return;
-    const float* xr = a.x + (int64_t)(f.x_compact ? item : b) * a.N;
+    const float* xr = f.x_offset ? a.x + f.x_offset[item] : a.x + (int64_t)(f.x_compact ? item : b) * a.N;
+    const int row_len = f.x_offset ? need : a.N;                          // samples that exist in this row
 
     // ---- A: audio + oscillator phases
-    const bool vec = ((reinterpret_cast<uintptr_t>(xr) & 15) == 0) && (n_base + kSeg <= a.N);
+    const bool vec = ((reinterpret_cast<uintptr_t>(xr) & 15) == 0) && (n_base + kSeg <= row_len);
     if (vec) {                                                            // 16-byte loads, 4 per thread
 #pragma unroll
         for (int k = 0; k < kSeg / 4 / kFusedThreads; ++k) {
@@ -566,7 +569,7 @@ __global__ void __launch_bounds__(kFusedThreads) phaser_fused_kernel(const Fused
     } else {
         for (int i = tid; i < kSeg; i += kFusedThreads) {
             const int n = n_base + i;
-            xs[i / kSub][i % kSub] = (n < a.N) ? __ldg(xr + n) : 0.0f;
+            xs[i / kSub][i % kSub] = (n < row_len) ? __ldg(xr + n) : 0.0f;
         }
     }
     const float two_pi = MODFX_TWO_PI_F;
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(kFusedThreads) phaser_fused_kernel(const Fused
         float* dr = f.dry_out + (int64_t)b * f.n_out;
         for (int i = tid; i < kSeg; i += kFusedThreads) {
             const int idx = n_base + i - start;
-            if (idx >= 0 && idx < f.n_out && n_base + i < a.N) dr[idx] = xs[i / kSub][i % kSub];
+            if (idx >= 0 && idx < f.n_out && n_base + i < row_len) dr[idx] = xs[i / kSub][i % kSub];
         }
     }
     __syncthreads();
@@ -812,7 +815,7 @@ extern "C" int64_t modfx_phaser_workspace_bytes(int32_t B, int64_t N) {
 
 namespace {
 
-int phaser_launch(const float* x, int x_compact, float* y, float* dry_out, int32_t B, int64_t N, int64_t n_out, const int32_t* start,
+int phaser_launch(const float* x, int x_compact, const int64_t* x_offset, float* y, float* dry_out, int32_t B, int64_t N, int64_t n_out, const int32_t* start,
                   float sr, const float* rate_hz, const float* depth, const float* centre_hz, const float* feedback,
                   const float* mix, int32_t block, const int32_t* example_index, int32_t n_items, void* workspace,
                   void* stream) {
@@ -841,7 +844,7 @@ int phaser_launch(const float* x, int x_compact, float* y, float* dry_out, int32
         // ---- single-pass fused kernel
         FusedArgs f{};
         f.a = a;
-        f.start = start; f.n_out = (int)n_out; f.dry_out = dry_out; f.x_compact = x_compact;
+        f.start = start; f.n_out = (int)n_out; f.dry_out = dry_out; f.x_compact = x_compact; f.x_offset = x_offset;
         f.n_seg = (int)((N + kSeg - 1) / kSeg);
         f.ticket = reinterpret_cast<int*>(w);                                     w += 256;
         f.flags = reinterpret_cast<int*>(w);
@@ -860,7 +863,7 @@ int phaser_launch(const float* x, int x_compact, float* y, float* dry_out, int32
         return MODFX_OK;
     }
     // ---- four-kernel pipeline (host blocks that are not a multiple of 128 samples; MODFX_PHASER_KERNEL=multi)
-    if (start || dry_out || n_out != N || x_compact)
+    if (start || dry_out || n_out != N || x_compact || x_offset)
         return fail(MODFX_ERR_UNSUPPORTED, "cropped output needs a host block size that is a multiple of %d samples", kChunk);
     a.C = reinterpret_cast<float*>(w);
     w += align_up((int64_t)a.n_items * a.n_ctl * 4, 256);
@@ -906,7 +909,7 @@ extern "C" int modfx_phaser_f32(const float* x, float* y, int32_t B, int64_t N, 
                                 const float* depth, const float* centre_hz, const float* feedback,
                                 const float* mix, int32_t block, const int32_t* example_index, int32_t n_items,
                                 void* workspace, void* stream) {
-    return phaser_launch(x, 0, y, nullptr, B, N, N, nullptr, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
+    return phaser_launch(x, 0, nullptr, y, nullptr, B, N, N, nullptr, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
                          n_items, workspace, stream);
 }
 
@@ -916,6 +919,17 @@ extern "C" int modfx_phaser_crop_f32(const float* x, int32_t x_compact, float* y
                                      const int32_t* example_index, int32_t n_items, void* workspace, void* stream) {
     MODFX_REQUIRE(start, "start is NULL");
     MODFX_REQUIRE(!x_compact || example_index, "x_compact needs an example_index list");
-    return phaser_launch(x, x_compact ? 1 : 0, y, dry_out, B, N, n_out, start, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
+    return phaser_launch(x, x_compact ? 1 : 0, nullptr, y, dry_out, B, N, n_out, start, sr, rate_hz, depth, centre_hz, feedback, mix, block, example_index,
                          n_items, workspace, stream);
+}
+
+extern "C" int modfx_phaser_crop_packed_f32(const float* x, const int64_t* x_offset, float* y, float* dry_out, int32_t B,
+                                            int64_t N_max, int64_t n_out, const int32_t* start, float sr, const float* rate_hz,
+                                            const float* depth, const float* centre_hz, const float* feedback, const float* mix,
+                                            int32_t block, const int32_t* example_index, int32_t n_items, void* workspace,
+                                            void* stream) {
+    MODFX_REQUIRE(start && x_offset, "start or x_offset is NULL");
+    MODFX_REQUIRE(example_index, "a packed x needs an example_index list (row i belongs to example example_index[i])");
+    return phaser_launch(x, 1, x_offset, y, dry_out, B, N_max, n_out, start, sr, rate_hz, depth, centre_hz, feedback, mix, block,
+                         example_index, n_items, workspace, stream);
 }

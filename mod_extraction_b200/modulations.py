@@ -195,7 +195,7 @@ def make_quasi_periodic(mod_sig: T,
 
 
 def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes: List[str], device=None,
-                                return_base: bool = False, host_replay: bool = False):
+                                return_base: bool = False, host_replay: bool = False, deferred: bool = False):
     """make_combined_mod_sig for B (freq, phase) pairs, equivalent to calling the reference function on pair 0, then
     pair 1, ... under the same state of the torch global CPU generator, which it leaves where that loop would.
 
@@ -204,7 +204,12 @@ def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes
     the GPU, one device thread replays the reference's draw order, and the generator is advanced by the number of
     words that replay consumed: one launch sequence and one 8-byte read-back for the whole batch instead of a python
     loop of scalar ``torch.randint`` calls (0.2 s for 4096 examples).  ``host_replay=True`` keeps that loop (the
-    cross-check of the device replay, and the fallback for signals with more than 64 bottom corners)."""
+    cross-check of the device replay, and the fallback for signals with more than 64 bottom corners).
+
+    ``deferred=True`` returns ``(out, finish)`` right after the launches: the caller queues whatever consumes ``out`` and
+    then calls ``finish()``, which performs the 8-byte read-back, advances the generator and returns True -- or False
+    when the device replay could not be used (more words or corners than provisioned: practically never), in which case
+    ``out`` is invalid, the generator is untouched and the caller falls back to the blocking call."""
     device = _device() if device is None else device
     f = tr.as_tensor(freqs, dtype=tr.float64).reshape(-1)
     p = tr.as_tensor(phases, dtype=tr.float64).reshape(-1)
@@ -213,6 +218,21 @@ def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes
     assert bool((f > 0.0).all()) and bool((f < sr / 2.0).all())             # modulations.py:23
     assert bool((p >= -2 * tr.pi).all()) and bool((p <= 2 * tr.pi).all())   # modulations.py:24
     sid = shape_ids(shapes)
+    if deferred:
+        assert not host_replay and not return_base and B > 0 and 3 <= n_samples <= 32767
+        from ._rng import TorchMT
+        mt = TorchMT()
+        words = tr.from_numpy(mt.words(B * 17).view("int32"))
+        out, _, consumed = _ops.combined_lfo(n_samples, sr, f.float().to(device, non_blocking=True),
+                                             p.float().to(device, non_blocking=True), sid.to(device),
+                                             words.to(device, non_blocking=True))
+
+        def finish() -> bool:
+            used, err = consumed.tolist()
+            if err == 0:
+                mt.consume(used)
+            return err == 0
+        return out, finish
     if not host_replay and B > 0 and 3 <= n_samples <= 32767:
         from ._rng import TorchMT
         mt = TorchMT()

@@ -77,43 +77,10 @@ class InterwovenRenderer:
         return wet, logmel
 
     # ------------------------------------------------------------------ the hot path
-    @torch.no_grad()
-    def render_host(self, dry_h: Tensor, effect: Tensor, mod_lo_h: Tensor, fc_h: Dict[str, Tensor],
-                    ph_h: Dict[str, Tensor], wet_h: Tensor, logmel: Tensor, stat_h: Optional[Tensor] = None,
-                    chunk: int = 512, dry_d: Optional[Tensor] = None, wet_d: Optional[Tensor] = None,
-                    logmel_h: Optional[Tensor] = None, ph_long_h: Optional[Tensor] = None,
-                    ph_start_h: Optional[Tensor] = None, dry_ph_h: Optional[Tensor] = None,
-                    dry_fc_h: Optional[Tensor] = None) -> None:
-        """Host-buffer entry point: pinned host dry audio + parameters in, wet audio out to the pinned host
-        tensor `wet_h`; the log-mel tensor stays on the GPU (`logmel`, (B,2,n_mels,n_frames)) where the
-        extractor consumes it, and `stat_h` (B, 2) receives its per-example mean; with `logmel_h` (pinned, same
-        shape) the log-mel tensor is delivered to the host as well.  `mod_lo_h` may already live on the device
-        (LFOs generated there).  `ph_long_h` (n_phaser, L) pinned + `ph_start_h` (B,) int32: the longer chunks of the
-        phaser examples and their window starts (see `render`); the dry windows cut out of them come back in
-        `dry_ph_h` (n_phaser, N) pinned, one row per phaser example in batch order (the rows of `dry_h` that belong to
-        phaser examples are then not read).  `dry_fc_h` (n_flanger + n_chorus, N) pinned: the dry audio of the other
-        examples as a compact array in batch order -- the per-effect layout the reference's three datasets produce --
-        in which case `dry_h` is not read at all (pass a (B, 1, N) meta / empty tensor for the shape) and the rows are
-        scattered into the interleaved batch on the device.  The batch is cut into chunks so that the H2D copy of chunk i+1, the kernels of
-        chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex); the call returns when everything has
-        landed."""
-        B, _, N = dry_h.shape
-        if dry_d is None:
-            dry_d = torch.empty((B, 1, N), device=self.device, dtype=torch.float32)
-        if wet_d is None:
-            wet_d = torch.empty((B, 1, N), device=self.device, dtype=torch.float32)
-        if not hasattr(self, "_io_streams"):
-            self._io_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
-        s_in, s_run, s_out = self._io_streams
-        cur = torch.cuda.current_stream(self.device)
-        start = torch.cuda.Event()
-        start.record(cur)                                   # e.g. LFOs generated on `cur` just before this call
-        for st in self._io_streams:
-            st.wait_event(start)
-        fc_keys = ("feedback", "min_delay_width", "width", "depth", "mix")
-        ph_keys = ("rate_hz", "depth", "centre_frequency_hz", "feedback", "mix")
-        # chunk schedule: a short first and last chunk keep the part of the pipeline that cannot overlap (the first
-        # H2D copy, the last D2H copy) small; everything in between moves `chunk` examples at a time
+    @staticmethod
+    def _chunk_edges(B: int, chunk: int):
+        """Chunk schedule of the host-buffer path: a short first and last chunk keep the part of the pipeline that cannot
+        overlap (the first H2D copy, the last kernels + D2H copy) small; everything in between moves `chunk` examples."""
         edges, lo = [], 0
         short = max(1, chunk // 4)
         while lo < B:
@@ -125,44 +92,128 @@ class InterwovenRenderer:
                 size = short
             edges.append((lo, lo + size))
             lo += size
-        cropped = ph_long_h is not None
+        return edges
+
+    @torch.no_grad()
+    def render_host(self, dry_h: Tensor, effect: Tensor, mod_lo_h, fc_h: Dict[str, Tensor],
+                    ph_h: Dict[str, Tensor], wet_h: Tensor, logmel: Tensor, stat_h: Optional[Tensor] = None,
+                    chunk: int = 512, dry_d: Optional[Tensor] = None, wet_d: Optional[Tensor] = None,
+                    logmel_h: Optional[Tensor] = None, ph_long_h: Optional[Tensor] = None,
+                    ph_start_h: Optional[Tensor] = None, dry_ph_h: Optional[Tensor] = None,
+                    dry_fc_h: Optional[Tensor] = None, ph_packed_h: Optional[Tensor] = None,
+                    ph_offsets=None) -> None:
+        """Host-buffer entry point: pinned host dry audio + parameters in, wet audio out to the pinned host
+        tensor `wet_h`; the log-mel tensor stays on the GPU (`logmel`, (B,2,n_mels,n_frames)) where the
+        extractor consumes it, and `stat_h` (B, 2) receives its per-example mean; with `logmel_h` (pinned, same
+        shape) the log-mel tensor is delivered to the host as well.
+
+        `mod_lo_h`: the (B, n_lo) control-rate LFOs -- a pinned host tensor, a device tensor, or a CALLABLE returning the
+        device tensor (LFO synthesis on the device): the callable runs after every input copy has been queued, so the
+        synthesis hides behind the first copies instead of delaying them.  The callable may also return
+        ``(tensor, finish)`` (``make_combined_mod_sig_batch(..., deferred=True)``): ``finish()`` -- the read-back that
+        advances the host generator -- is then called after all the work of the step has been queued; if it returns
+        False the whole step is redone with ``mod_lo_h(blocking=True)``.
+        Phaser examples (rendered over a longer chunk and cropped, see `render`) come either as `ph_long_h`
+        (n_phaser, L) pinned rows of a common pitch, or -- what a collate function produces from the variable-length
+        chunks the reference's dataset reads -- as `ph_packed_h`, a 1-D pinned array of the rows back to back, with
+        `ph_offsets` (n_phaser + 1 host ints, multiples of 4) their starts; row i then only needs its first
+        start + N samples, the causal prefix that determines the window.  `ph_start_h` (B,) int32: the window starts.
+        The dry windows cut out of the phaser chunks are written into the phaser rows of `dry_d` on the device (the
+        log-mel needs them); they are views of host data the caller already has, so they are only copied back when
+        `dry_ph_h` (n_phaser, N) pinned is given.  `dry_fc_h` (n_flanger + n_chorus, N) pinned: the dry audio of the other
+        examples as a compact array in batch order -- the per-effect layout the reference's three datasets produce --
+        in which case `dry_h` is not read at all (pass a (B, 1, N) meta / empty tensor for the shape) and the rows are
+        scattered into the interleaved batch on the device.
+
+        Schedule: ALL input copies are queued first on the copy-in stream (one event per chunk), then per chunk the
+        kernels (compute stream) and the output copies (copy-out stream), so the H2D engine never waits for the host
+        and the H2D copy of chunk i+k, the kernels of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full
+        duplex); the call returns when everything has landed."""
+        B, _, N = dry_h.shape
+        dev = self.device
+        if dry_d is None:
+            dry_d = torch.empty((B, 1, N), device=dev, dtype=torch.float32)
+        if wet_d is None:
+            wet_d = torch.empty((B, 1, N), device=dev, dtype=torch.float32)
+        if not hasattr(self, "_io_streams"):
+            self._io_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        s_in, s_run, s_out = self._io_streams
+        cur = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(cur)                                   # whatever the caller queued before this call
+        for st in self._io_streams:
+            st.wait_event(start)
+        fc_keys = ("feedback", "min_delay_width", "width", "depth", "mix")
+        ph_keys = ("rate_hz", "depth", "centre_frequency_hz", "feedback", "mix")
+        edges = self._chunk_edges(B, chunk)
+        packed = ph_packed_h is not None
+        cropped = packed or ph_long_h is not None
+        assert not (packed and ph_long_h is not None), "phaser chunks come packed OR padded"
         if cropped:
             assert ph_start_h is not None
             is_ph = (effect.detach().reshape(-1).cpu() == PHASER)
             ph_before = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(is_ph.to(torch.int64), 0)]).tolist()
-        assert dry_fc_h is None or cropped, "dry_fc_h goes with ph_long_h"
-        for lo, hi in edges:
-            with torch.cuda.stream(s_in):
+        if packed:
+            offs = [int(v) for v in ph_offsets]
+            assert len(offs) == ph_before[B] + 1 and all(o % 4 == 0 for o in offs), "ph_offsets: n_phaser + 1 multiples of 4"
+            max_len = int(ph_start_h.max()) + N if ph_start_h.numel() else N
+        assert dry_fc_h is None or cropped, "dry_fc_h goes with the phaser chunks"
+        keep = []                                           # device buffers that must outlive the queued work
+
+        # ---- 1. every input copy, in chunk order, on the copy-in stream
+        staged = []
+        with torch.cuda.stream(s_in):
+            f_all = {k: fc_h[k].to(dev, non_blocking=True) for k in fc_keys}
+            p_all = {k: ph_h[k].to(dev, non_blocking=True) for k in ph_keys}
+            pst_all = ph_start_h.to(dev, non_blocking=True) if cropped else None
+            offs_all = torch.tensor(offs, dtype=torch.int64).pin_memory().to(dev, non_blocking=True) if packed else None
+            m_all = None
+            if not callable(mod_lo_h):
+                m_all = mod_lo_h if mod_lo_h.is_cuda else mod_lo_h.to(dev, non_blocking=True)
+            for lo, hi in edges:
                 if dry_fc_h is None:
                     dry_d[lo:hi].copy_(dry_h[lo:hi], non_blocking=True)
                 else:
                     f0, f1 = lo - ph_before[lo], hi - ph_before[hi]
-                    stage = dry_fc_h[f0:f1].to(self.device, non_blocking=True)
+                    stage = dry_fc_h[f0:f1].to(dev, non_blocking=True)
                     dry_d[lo:hi].view(hi - lo, N).index_copy_(0, self._groups(effect, lo, hi)[3], stage)
-                    stage.record_stream(s_in)
-                pl = pst = None
+                    keep.append(stage)
+                pl = po = None
+                r0 = r1 = 0
                 if cropped:
                     r0, r1 = ph_before[lo], ph_before[hi]
-                    pl = ph_long_h[r0:r1].to(self.device, non_blocking=True)
-                    pst = ph_start_h[lo:hi].to(self.device, non_blocking=True)
-                m = mod_lo_h[lo:hi] if mod_lo_h.is_cuda else mod_lo_h[lo:hi].to(self.device, non_blocking=True)
-                f = {k: fc_h[k][lo:hi].to(self.device, non_blocking=True) for k in fc_keys}
-                p = {k: ph_h[k][lo:hi].to(self.device, non_blocking=True) for k in ph_keys}
+                    if packed:
+                        pl = ph_packed_h[offs[r0]:offs[r1]].to(dev, non_blocking=True)
+                        po = offs_all[r0:r1] - offs[r0]
+                    else:
+                        pl = ph_long_h[r0:r1].to(dev, non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(s_in)
+                staged.append((ev_in, pl, po, r0, r1))
+        keep += [*f_all.values(), *p_all.values(), pst_all, offs_all]
+
+        # ---- 2. per chunk: kernels, then the output copies
+        with torch.cuda.stream(s_run):
+            finish = None
+            if callable(mod_lo_h):
+                m_all = mod_lo_h()                          # device-side LFO synthesis, behind the first input copies
+                if isinstance(m_all, tuple):
+                    m_all, finish = m_all
+        for (lo, hi), (ev_in, pl, po, r0, r1) in zip(edges, staged):
             s_run.wait_event(ev_in)
             with torch.cuda.stream(s_run):
-                self.render(dry_d[lo:hi], effect, m, f, p, wet=wet_d[lo:hi], logmel=logmel[lo:hi], _range=(lo, hi),
-                            ph_long=pl, ph_start=pst)
+                f = {k: v[lo:hi] for k, v in f_all.items()}
+                p = {k: v[lo:hi] for k, v in p_all.items()}
+                self.render(dry_d[lo:hi], effect, m_all[lo:hi], f, p, wet=wet_d[lo:hi], logmel=logmel[lo:hi], _range=(lo, hi),
+                            ph_long=pl, ph_start=None if pst_all is None else pst_all[lo:hi], ph_offsets=po,
+                            ph_max_len=max_len if packed else None)
                 st_d = logmel[lo:hi].mean(dim=(2, 3)) if stat_h is not None else None
                 dph = None
                 if cropped and dry_ph_h is not None and r1 > r0:
                     dph = dry_d[lo:hi].view(hi - lo, N).index_select(0, self._groups(effect, lo, hi)[2].to(torch.int64))
                 ev_run = torch.cuda.Event()
                 ev_run.record(s_run)
-                for t in (m, *f.values(), *p.values(), pl, pst):
-                    if t is not None:
-                        t.record_stream(s_run)
+            keep += [pl, po]
             s_out.wait_event(ev_run)
             with torch.cuda.stream(s_out):
                 wet_h[lo:hi].copy_(wet_d[lo:hi], non_blocking=True)
@@ -170,21 +221,28 @@ class InterwovenRenderer:
                     logmel_h[lo:hi].copy_(logmel[lo:hi], non_blocking=True)
                 if stat_h is not None:
                     stat_h[lo:hi].copy_(st_d, non_blocking=True)
-                    st_d.record_stream(s_out)
+                    keep.append(st_d)
                 if dph is not None:
                     dry_ph_h[r0:r1].copy_(dph, non_blocking=True)
-                    dph.record_stream(s_out)
+                    keep.append(dph)
         for st in self._io_streams:
             ev = torch.cuda.Event()
             ev.record(st)
             cur.wait_event(ev)
-        cur.synchronize()
+        ok = finish() if finish is not None else True       # read-back of the LFO synthesis, behind everything queued
+        cur.synchronize()                                   # everything has landed: `keep` may go
+        del keep
+        if not ok:
+            m = mod_lo_h(blocking=True)
+            self.render_host(dry_h, effect, m, fc_h, ph_h, wet_h, logmel, stat_h, chunk, dry_d, wet_d, logmel_h, ph_long_h,
+                             ph_start_h, dry_ph_h, dry_fc_h, ph_packed_h, ph_offsets)
 
     @torch.no_grad()
     def render(self, dry: Tensor, effect: Tensor, mod_lo: Tensor, fc: Dict[str, Tensor], ph: Dict[str, Tensor],
                wet: Optional[Tensor] = None, logmel: Optional[Tensor] = None,
                _range: Optional[Tuple[int, int]] = None, ph_long: Optional[Tensor] = None,
-               ph_start: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+               ph_start: Optional[Tensor] = None, ph_offsets: Optional[Tensor] = None,
+               ph_max_len: Optional[int] = None) -> Tuple[Tensor, Tensor]:
         """dry (B,1,N) CUDA float32; effect (B,) ints in {0: flanger, 1: chorus, 2: phaser};
         mod_lo (B, n_lo) control-rate LFO of the flanger / chorus examples (rows of phaser examples are
         ignored); fc: feedback, min_delay_width, width, depth, mix as (B,) tensors (data_modules.py:421-445);
@@ -196,7 +254,9 @@ class InterwovenRenderer:
         one row per phaser example in batch order, and ``ph_start`` (B,) the window starts: the phaser then runs over the
         long rows and writes the window of its wet output into ``wet`` AND the same window of the dry chunk into the
         phaser rows of ``dry`` (in place), before their log-mel is taken.  Without ``ph_long`` the phaser rows of ``dry``
-        are rendered as they are (no extra period)."""
+        are rendered as they are (no extra period).  With ``ph_offsets`` (int64, one per phaser example) ``ph_long`` is a
+        packed 1-D array instead: row i starts at ``ph_long[ph_offsets[i]]`` and holds its first ``start + N`` samples;
+        ``ph_max_len`` bounds ``start + N``."""
         assert dry.is_cuda and dry.dtype == torch.float32 and dry.ndim == 3 and dry.size(1) == 1
         assert dry.is_contiguous()
         B, _, N = dry.shape
@@ -214,7 +274,8 @@ class InterwovenRenderer:
         lm_dry, lm_wet = logmel.view(-1), logmel.view(-1)[nm:]
         cropped = ph_long is not None and i_ph.numel() > 0
         if cropped:
-            assert ph_start is not None and ph_long.is_cuda and ph_long.shape[0] == i_ph.numel() and ph_start.numel() == B
+            assert ph_start is not None and ph_long.is_cuda and ph_start.numel() == B
+            assert (ph_long.shape[0] == i_ph.numel()) if ph_offsets is None else (ph_offsets.numel() == i_ph.numel())
 
         def effects_fl():
             _ops.flanger_chorus(dry, src, self.fl[0], self.fl[1], *fc_args, example_index=i_fl, out=wet)
@@ -225,7 +286,7 @@ class InterwovenRenderer:
         def effects_ph():
             if cropped:
                 _ops.phaser_crop(ph_long, N, ph_start, self.sr, *ph_args, block=self.phaser_buffer_size,
-                                 example_index=i_ph, out=wet2, dry_out=dry2)
+                                 example_index=i_ph, out=wet2, dry_out=dry2, row_offsets=ph_offsets, max_len=ph_max_len)
             else:
                 _ops.phaser(dry2, self.sr, *ph_args, block=self.phaser_buffer_size, example_index=i_ph, out=wet2)
 
@@ -264,7 +325,7 @@ class InterwovenRenderer:
             fin = torch.cuda.Event()
             fin.record(s_dry)
         cur.wait_event(fin)
-        for t in (dry, mod_lo, wet, logmel, ph_long, ph_start, *fc_args, *ph_args):
+        for t in (dry, mod_lo, wet, logmel, ph_long, ph_start, ph_offsets, *fc_args, *ph_args):
             if isinstance(t, Tensor) and t.is_cuda:
                 for s in self._streams:
                     t.record_stream(s)

@@ -156,3 +156,51 @@ def test_render_host_grouped_buffers_equal_device_render():
     assert torch.equal(wet_h, w_ref.cpu()) and torch.equal(lm, lm_ref)
     assert torch.equal(dry_ph_h, d_ref.cpu()[phx, 0])
     assert torch.allclose(stat_h, lm_ref.mean(dim=(2, 3)).cpu(), atol=1e-5)
+
+
+def test_render_host_packed_phaser_rows_and_lfo_callable():
+    """Host-buffer entry point fed like a collate function would: the phaser chunks packed back to back, each cut to the
+    start + N samples that determine its window (garbage behind them must not matter), the LFOs produced by a callable on
+    the device.  Result == one device render of the padded rows, bit for bit; the dry windows only when asked for."""
+    from mod_extraction_b200.render import InterwovenRenderer
+    dev = torch.device("cuda", 0)
+    B = 26
+    dry, effect, mod_lo, fc, ph = bench.oracle_inputs(B, seed=11)
+    rng = np.random.RandomState(5)
+    phx, fcx = np.nonzero(effect == 2)[0], np.nonzero(effect != 2)[0]
+    extra = (bench.SR / ph["rate_hz"] + 0.5).astype(np.int64)
+    L = bench.N + int(extra[phx].max())
+    long_rows = ((rng.random_sample((phx.size, L)) * 2 - 1) * 0.5).astype(np.float32)
+    start = np.zeros(B, dtype=np.int32)
+    start[phx] = [rng.randint(0, extra[b] + 1) for b in phx]
+    start[phx[0]], start[phx[-1]] = 0, extra[phx[-1]]                     # shortest and longest possible prefix
+    lens = (start[phx].astype(np.int64) + bench.N + 3) // 4 * 4
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    packed = np.full((int(offs[-1]),), np.nan, dtype=np.float32)
+    for i in range(phx.size):
+        n = int(start[phx[i]]) + bench.N
+        packed[offs[i]:offs[i] + n] = long_rows[i, :n]                    # the alignment padding stays NaN: never read
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    R = InterwovenRenderer(bench.N, float(bench.SR), dev)
+    eff = torch.from_numpy(effect)
+    d_ref = to(dry)
+    w_ref, lm_ref = R.render(d_ref, eff, to(mod_lo), {k: to(v) for k, v in fc.items()}, {k: to(v) for k, v in ph.items()},
+                             ph_long=to(long_rows), ph_start=to(start))
+    torch.cuda.synchronize()
+    for want_dry in (False, True):
+        wet_h = torch.empty((B, 1, bench.N)).pin_memory()
+        dry_ph_h = torch.empty((phx.size, bench.N)).pin_memory() if want_dry else None
+        _, lm = R.alloc_outputs(B)
+        calls = []
+
+        def lfos():
+            calls.append(1)
+            return to(mod_lo)
+        R.render_host(torch.empty((B, 1, bench.N), device="meta"), eff, lfos, {k: pin(v) for k, v in fc.items()},
+                      {k: pin(v) for k, v in ph.items()}, wet_h, lm, None, chunk=5, ph_packed_h=pin(packed), ph_offsets=offs,
+                      ph_start_h=pin(start), dry_ph_h=dry_ph_h, dry_fc_h=pin(dry[fcx, 0]))
+        assert len(calls) == 1
+        assert torch.equal(wet_h, w_ref.cpu()) and torch.equal(lm, lm_ref)
+        if want_dry:
+            assert torch.equal(dry_ph_h, d_ref.cpu()[phx, 0])

@@ -93,3 +93,21 @@ def test_combined_device_replay_equals_host_replay(B, seed):
     assert torch.equal(base_slow.cpu(), base_fast.cpu())
     assert torch.equal(slow, fast)
     assert torch.equal(next_slow, next_fast), "the generator must end where the reference's loop leaves it"
+
+
+def test_combined_deferred_read_back_equals_blocking_call():
+    """deferred=True hands the signals back before the 8-byte read-back; finish() then leaves the generator where the
+    blocking call does."""
+    from mod_extraction_b200.modulations import make_combined_mod_sig_batch
+    rng = np.random.RandomState(8)
+    f = np.exp(rng.uniform(np.log(1.0), np.log(3.0), 300))
+    ph = rng.uniform(0, 2 * np.pi, 300)
+    torch.manual_seed(21)
+    ref = make_combined_mod_sig_batch(882, 441, f, ph, SHAPES6)
+    next_ref = torch.rand(5)
+    torch.manual_seed(21)
+    out, finish = make_combined_mod_sig_batch(882, 441, f, ph, SHAPES6, deferred=True)
+    doubled = out * 2                                           # work queued before the read-back
+    assert finish() is True
+    assert torch.equal(out, ref) and torch.equal(doubled, ref * 2)
+    assert torch.equal(torch.rand(5), next_ref)
