@@ -207,7 +207,7 @@ extern "C" int modfx_stretch_sections_f32(const float* in, float* out, int32_t B
 //   1. every candidate base shape of every example is rendered (combined_cand_kernel);
 //   2. the bottom corners of every candidate are listed (corner_list_kernel, one warp per row);
 //   3. ONE thread walks the examples in order: base = shapes[word % S], sections = corners - 1, next example starts
-//      1 + sections words later (combined_scan_kernel) -- integer work only, ~100 cycles per example;
+//      1 + sections words later (combined_scan_kernel) -- integer work only, fed from shared memory;
 //   4. every example takes its base candidate and overwrites the spans with make_mod_signal(len, len, 1.0, 0.0, shape)
 //      (combined_fill_kernel; later spans win at shared end points like the reference's in-order slice assignment).
 // The number of words consumed comes back so the host can advance the generator by exactly that much.
@@ -257,26 +257,67 @@ __global__ void __launch_bounds__(128) corner_list_kernel(const float* __restric
     if (lane == 0) cnt[row] = c;
 }
 
-__global__ void combined_scan_kernel(const uint32_t* __restrict__ words, int64_t n_words, const int32_t* __restrict__ cnt,
-                                     int B, int S, int32_t* __restrict__ base, int32_t* __restrict__ woff,
-                                     int32_t* __restrict__ consumed) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int64_t off = 0;
-    int err = 0;
-    for (int b = 0; b < B; ++b) {
-        woff[b] = (int32_t)off;
-        if (off >= n_words) { err = 1; base[b] = 0; continue; }
-        const int k = (int)(words[off] % (uint32_t)S);                  // util.choice(shapes), modulations.py:196
-        base[b] = k;
-        const int c = cnt[b * S + k];
-        if (c > kMaxCorners) err = 2;
-        const int nsec = (c > 1) ? c - 1 : 0;                           // modulations.py:203-204
-        off += 1 + nsec;
+// Step 3: the chain  off(b+1) = off(b) + 1 + sections(b, words[off(b)] % S)  is serial by construction.  One CTA stages
+// what the chain touches in shared memory -- the corner counts of a tile of examples (all S candidates) and a window of
+// generator words starting at the current offset -- and thread 0 walks the tile at shared-memory latency (two dependent
+// loads and one modulo per example instead of two dependent L2 round trips: 2 ms -> 0.2 ms for 4096 examples).
+constexpr int kScanThreads = 256;
+constexpr int kScanWords = 8192;            // words staged per window (32 KB)
+constexpr int kScanCnt = 8192;              // corner counts staged per tile (one byte each)
+
+__global__ void __launch_bounds__(kScanThreads) combined_scan_kernel(const uint32_t* __restrict__ words, int64_t n_words,
+                                                                     const int32_t* __restrict__ cnt, int B, int S,
+                                                                     int32_t* __restrict__ base, int32_t* __restrict__ woff,
+                                                                     int32_t* __restrict__ consumed) {
+    __shared__ uint32_t sw[kScanWords];
+    __shared__ uint8_t sc[kScanCnt];
+    __shared__ long long s_off;
+    __shared__ int s_b, s_err;
+    const int tid = threadIdx.x;
+    const int tile = max(1, kScanCnt / S);                              // examples per tile
+    if (tid == 0) { s_off = 0; s_b = 0; s_err = 0; }
+    __syncthreads();
+    int tile_lo = -1;
+    while (true) {
+        const int b0 = s_b;
+        const long long off0 = s_off;
+        if (b0 >= B) break;
+        const int t_lo = b0 / tile * tile, t_hi = min(t_lo + tile, B);
+        if (t_lo != tile_lo) {                                          // corner counts of this tile, saturated at 255
+            for (int i = tid; i < (t_hi - t_lo) * S; i += kScanThreads) sc[i] = (uint8_t)min(cnt[(int64_t)t_lo * S + i], 255);
+            tile_lo = t_lo;
+        }
+        const int n_win = (int)min((long long)kScanWords, (long long)n_words - off0);
+        for (int i = tid; i < n_win; i += kScanThreads) sw[i] = words[off0 + i];
+        __syncthreads();
+        if (tid == 0) {
+            long long off = off0;
+            int b = b0, err = s_err;
+            for (; b < t_hi; ++b) {
+                if (off >= n_words) {                                   // out of words: flag it, the rest gets base 0
+                    err = err ? err : 1;
+                    woff[b] = (int32_t)off;
+                    base[b] = 0;
+                    continue;
+                }
+                if (off - off0 >= n_win) break;                         // next window
+                woff[b] = (int32_t)off;
+                const int k = (int)(sw[off - off0] % (uint32_t)S);      // util.choice(shapes), modulations.py:196
+                base[b] = k;
+                const int c = sc[(b - t_lo) * S + k];
+                if (c > kMaxCorners) err = 2;
+                off += 1 + ((c > 1) ? c - 1 : 0);                       // modulations.py:203-204
+            }
+            s_off = off; s_b = b; s_err = err;
+        }
+        __syncthreads();
     }
-    if (off > n_words) err = 1;
-    woff[B] = (int32_t)off;
-    consumed[0] = (int32_t)off;
-    consumed[1] = err;
+    if (tid == 0) {
+        const long long off = s_off;
+        woff[B] = (int32_t)off;
+        consumed[0] = (int32_t)off;
+        consumed[1] = (off > n_words && s_err == 0) ? 1 : s_err;
+    }
 }
 
 __global__ void __launch_bounds__(256) combined_fill_kernel(float* __restrict__ out, int n, const float* __restrict__ cand,
@@ -341,7 +382,7 @@ extern "C" int modfx_combined_lfo_f32(float* out, int32_t B, int64_t n, float sr
     MODFX_REQUIRE(rows <= 65535, "B * n_shapes = %lld exceeds grid.y", (long long)rows);
     combined_cand_kernel<<<dim3(gx, (unsigned)rows), 256, 0, s>>>(cand, (int)n, sr, freq, phase, shapes, n_shapes);
     corner_list_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(cand, (int)rows, (int)n, idx, cnt);
-    combined_scan_kernel<<<1, 32, 0, s>>>(words, n_words, cnt, B, n_shapes, base_out, woff, consumed_out);
+    combined_scan_kernel<<<1, kScanThreads, 0, s>>>(words, n_words, cnt, B, n_shapes, base_out, woff, consumed_out);
     combined_fill_kernel<<<dim3(gx, (unsigned)B), 256, 0, s>>>(out, (int)n, cand, idx, cnt, base_out, woff, words, shapes, n_shapes);
     MODFX_CUDA_OK(cudaGetLastError());
     return MODFX_OK;
