@@ -435,8 +435,10 @@ def make_e2e_step(cx, R, wb, chunk):
     dry_fc_h = pin(dry.view(B, N).index_select(0, i_fc))                        # dry audio of the flanger / chorus examples
     fc_h = {k: pin(v) for k, v in wb["fc"].items()}
     ph_h = {k: pin(v) for k, v in wb["ph"].items()}
-    wet_h = torch.empty((B, 1, N), dtype=torch.float32).pin_memory()
-    stat_h = torch.empty((B, 2), dtype=torch.float32).pin_memory()
+    # two sets of pinned output buffers: consecutive steps alternate between them when they are pipelined
+    wet_hs = [torch.empty((B, 1, N), dtype=torch.float32).pin_memory() for _ in range(2)]
+    stat_hs = [torch.empty((B, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    wet_h, stat_h = wet_hs[0], stat_hs[0]
     dry_d = torch.empty_like(dry)
     # the phaser chunks as a collate function would hand them over: variable-length rows back to back (16-byte aligned
     # starts), each cut to the prefix that determines its window (start + N samples; the effect is causal)
@@ -458,11 +460,11 @@ def make_e2e_step(cx, R, wb, chunk):
         torch.manual_seed(43 + rank)
         return make_combined_mod_sig_batch(n_lo, SR // 100, wb["rate"], wb["phase"], SHAPES6, device=dev, deferred=not blocking)
 
-    def e2e_step(logmel_h=None):
+    def e2e_step(logmel_h=None, wait=True, alt=0):
         # host (rate, phase) + generator state in, pinned dry audio in; wet audio (+ log-mel) out to pinned host
-        R.render_host(dry_h, wb["effect"], lfos, fc_h, ph_h, wet_h, logmel, stat_h, chunk=chunk,
-                      dry_d=dry_d, wet_d=wet, logmel_h=logmel_h, ph_packed_h=ph_packed_h, ph_offsets=offs,
-                      ph_start_h=ph_start_h, dry_fc_h=dry_fc_h)
+        return R.render_host(dry_h, wb["effect"], lfos, fc_h, ph_h, wet_hs[alt], logmel, stat_hs[alt], chunk=chunk,
+                             dry_d=dry_d, wet_d=wet, logmel_h=logmel_h, ph_packed_h=ph_packed_h, ph_offsets=offs,
+                             ph_start_h=ph_start_h, dry_fc_h=dry_fc_h, wait=wait)
     return e2e_step, {"h2d": h2d, "d2h": d2h}
 
 
@@ -502,14 +504,16 @@ def run_config4(cx, args):
     # ---------------- the same step with the LFO synthesis inside it (north_star puts it on the hot path)
     def step_with_lfo():
         torch.manual_seed(43 + rank)
-        wb["mod_lo"] = make_combined_mod_sig_batch(n_lo, SR // 100, wb["rate"], wb["phase"], SHAPES6, device=dev)
+        wb["mod_lo"], finish = make_combined_mod_sig_batch(n_lo, SR // 100, wb["rate"], wb["phase"], SHAPES6, device=dev,
+                                                           deferred=True)
         step()
+        assert finish()             # waits for the LFO kernels only: the next step's host work overlaps this render
     ms_lfo, _ = cx.timed(step_with_lfo, args.steps, 3)
     with_lfo = {"value": world * B * (N / SR) / (ms_lfo * 1e-3), "ms_per_step": ms_lfo,
                 "lfo_ms": max(0.0, ms_lfo - ms_per_step),
                 "note": "combined-shape control-rate LFOs regenerated every step from (rate, phase) and the torch global "
                         "generator: candidates + corner search + draw-order replay + span synthesis on the device, one "
-                        "8-byte read-back (modulations.make_combined_mod_sig_batch)"}
+                        "8-byte read-back taken after the render has been queued (make_combined_mod_sig_batch(deferred=True))"}
 
     # ---------------- per-kernel durations, serialised (same launches, one stream) for the roofline
     Rs = InterwovenRenderer(N, float(SR), dev, concurrent=False)
@@ -562,17 +566,42 @@ def run_config4(cx, args):
             cx.barrier()
             return cx.max_over_ranks((time.perf_counter() - t0) / n_rep)
 
+        def host_timed_pipelined(n_rep):
+            """Steady-state step time with consecutive steps overlapped: step i+1 is queued (its input copies start)
+            while the last output copies of step i drain; every step's copies, kernels and read-back are inside the
+            timed region, which ends when the last byte of the last step has landed."""
+            def burst(n):
+                h = None
+                for i in range(n):
+                    nxt = e2e_step(wait=False, alt=i & 1)
+                    if h is not None:
+                        h.wait()
+                    h = nxt
+                h.wait()
+            burst(2)
+            cx.barrier()
+            t0 = time.perf_counter()
+            burst(n_rep)
+            cx.barrier()
+            return cx.max_over_ranks((time.perf_counter() - t0) / n_rep)
+
         n_e2e = max(3, min(args.steps, 10))
-        dt = host_timed(e2e_step, n_e2e)
+        dt_serial = host_timed(e2e_step, n_e2e)
+        dt = host_timed_pipelined(n_e2e)
         e2e = {"value": world * B * (N / SR) / dt, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": n_e2e, "chunk": args.e2e_chunk,
+               "one_step_alone": {"ms": dt_serial * 1e3, "value": world * B * (N / SR) / dt_serial,
+                                  "note": "the same call with every step synchronised before the next one starts (latency of "
+                                          "one step: first input byte to last output byte)"},
                "note": "per step, InterwovenRenderer.render_host: pinned host dry audio of the flanger / chorus examples + the "
                        "variable-length chunks of the phaser examples (packed back to back, each cut to the start + N samples "
                        "that determine its window) + parameters in, LFO synthesis on the device from host (rate, phase) + "
                        "generator words behind the first copies, wet audio + per-example log-mel mean out (the dry windows of "
                        "the phaser examples are slices of host data and are not copied back), chunks pipelined over "
-                       "copy/compute/copy streams; the (B,2,256,345) log-mel tensor stays in HBM where the extractor consumes "
-                       "it (e2e_full delivers it to the host too)"}
+                       "copy/compute/copy streams and consecutive steps pipelined the same way (render_host(wait=False): step "
+                       "i+1 is queued while the last output copies of step i drain, two alternating sets of pinned output "
+                       "buffers; timed from the first call to the last byte of the last step); the (B,2,256,345) log-mel "
+                       "tensor stays in HBM where the extractor consumes it (e2e_full delivers it to the host too)"}
         if not args.no_e2e_full:
             try:
                 logmel_h = torch.empty(tuple(logmel.shape), dtype=torch.float32).pin_memory()

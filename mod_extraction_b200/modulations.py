@@ -194,6 +194,9 @@ def make_quasi_periodic(mod_sig: T,
     return out.cpu() if on_cpu else out
 
 
+_PINNED_PAIRS: list = []        # recycled pinned (2,) int32 buffers of the deferred read-back
+
+
 def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes: List[str], device=None,
                                 return_base: bool = False, host_replay: bool = False, deferred: bool = False):
     """make_combined_mod_sig for B (freq, phase) pairs, equivalent to calling the reference function on pair 0, then
@@ -227,8 +230,17 @@ def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes
                                              p.float().to(device, non_blocking=True), sid.to(device),
                                              words.to(device, non_blocking=True))
 
+        # the read-back is queued right behind the replay (pinned destination + event), so finish() waits for the LFO
+        # kernels only, not for whatever the caller queues after them
+        back = _PINNED_PAIRS.pop() if _PINNED_PAIRS else tr.empty((2,), dtype=tr.int32).pin_memory()
+        back.copy_(consumed, non_blocking=True)
+        landed = tr.cuda.Event()
+        landed.record()
+
         def finish() -> bool:
-            used, err = consumed.tolist()
+            landed.synchronize()
+            used, err = back.tolist()
+            _PINNED_PAIRS.append(back)
             if err == 0:
                 mt.consume(used)
             return err == 0

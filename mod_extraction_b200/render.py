@@ -26,6 +26,23 @@ from .models import LogMelSpectrogram
 FLANGER, CHORUS, PHASER = 0, 1, 2       # order of configs/data/interwoven_idmt_all.yml
 
 
+class _HostStep:
+    """One queued host-buffer step (InterwovenRenderer.render_host(wait=False))."""
+
+    def __init__(self, end_events, keep, stream) -> None:
+        self._end, self._keep, self._stream = end_events, keep, stream
+
+    def wait(self) -> None:
+        """Blocks until every output of the step has landed in its host buffer; later work on the caller's stream is
+        ordered behind the step as well."""
+        if self._end is None:
+            return
+        for ev in self._end:
+            self._stream.wait_event(ev)
+            ev.synchronize()
+        self._end, self._keep = None, None                  # device staging buffers may go back to the allocator
+
+
 class InterwovenRenderer:
     def __init__(self, n_samples: int = 88200, sr: float = 44100.0, device=None,
                  flanger_delays_ms: Tuple[float, float] = (1.0, 10.0),      # configs/data/gen_idmt_fl.yml
@@ -101,7 +118,7 @@ class InterwovenRenderer:
                     logmel_h: Optional[Tensor] = None, ph_long_h: Optional[Tensor] = None,
                     ph_start_h: Optional[Tensor] = None, dry_ph_h: Optional[Tensor] = None,
                     dry_fc_h: Optional[Tensor] = None, ph_packed_h: Optional[Tensor] = None,
-                    ph_offsets=None) -> None:
+                    ph_offsets=None, wait: bool = True):
         """Host-buffer entry point: pinned host dry audio + parameters in, wet audio out to the pinned host
         tensor `wet_h`; the log-mel tensor stays on the GPU (`logmel`, (B,2,n_mels,n_frames)) where the
         extractor consumes it, and `stat_h` (B, 2) receives its per-example mean; with `logmel_h` (pinned, same
@@ -125,10 +142,16 @@ class InterwovenRenderer:
         in which case `dry_h` is not read at all (pass a (B, 1, N) meta / empty tensor for the shape) and the rows are
         scattered into the interleaved batch on the device.
 
-        Schedule: ALL input copies are queued first on the copy-in stream (one event per chunk), then per chunk the
-        kernels (compute stream) and the output copies (copy-out stream), so the H2D engine never waits for the host
-        and the H2D copy of chunk i+k, the kernels of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full
-        duplex); the call returns when everything has landed."""
+        Schedule: the input copies are queued ahead of everything else on the copy-in stream (one event per chunk), then
+        per chunk the kernels (compute stream) and the output copies (copy-out stream), so the H2D engine never waits for
+        the host and the H2D copy of chunk i+k, the kernels of chunk i and the D2H copy of chunk i-1 overlap (PCIe is
+        full duplex); the call returns when everything has landed.
+
+        ``wait=False`` returns a handle right after queuing instead (``handle.wait()`` blocks until this step's outputs
+        have landed): the next call may be issued before that, and its input copies then run while this step's last
+        output copies drain -- consecutive steps are pipelined like chunks are.  The device buffers ``dry_d`` / ``wet_d``
+        / ``logmel`` may be the same in consecutive calls (per-chunk events order the reuse); the HOST output buffers
+        must not be read before ``handle.wait()`` and should alternate between two sets when steps overlap."""
         B, _, N = dry_h.shape
         dev = self.device
         if dry_d is None:
@@ -143,6 +166,7 @@ class InterwovenRenderer:
         start.record(cur)                                   # whatever the caller queued before this call
         for st in self._io_streams:
             st.wait_event(start)
+        prev = getattr(self, "_prev_host_step", None)       # a step that may still be in flight (wait=False)
         fc_keys = ("feedback", "min_delay_width", "width", "depth", "mix")
         ph_keys = ("rate_hz", "depth", "centre_frequency_hz", "feedback", "mix")
         edges = self._chunk_edges(B, chunk)
@@ -160,8 +184,7 @@ class InterwovenRenderer:
         assert dry_fc_h is None or cropped, "dry_fc_h goes with the phaser chunks"
         keep = []                                           # device buffers that must outlive the queued work
 
-        # ---- 1. every input copy, in chunk order, on the copy-in stream
-        staged = []
+        # ---- input copies of one chunk on the copy-in stream
         with torch.cuda.stream(s_in):
             f_all = {k: fc_h[k].to(dev, non_blocking=True) for k in fc_keys}
             p_all = {k: ph_h[k].to(dev, non_blocking=True) for k in ph_keys}
@@ -170,7 +193,19 @@ class InterwovenRenderer:
             m_all = None
             if not callable(mod_lo_h):
                 m_all = mod_lo_h if mod_lo_h.is_cuda else mod_lo_h.to(dev, non_blocking=True)
-            for lo, hi in edges:
+        keep += [*f_all.values(), *p_all.values(), pst_all, offs_all]
+
+        same_plan = prev is not None and prev["edges"] == edges
+        if prev is not None and not same_plan:              # other chunking: order behind the whole previous step
+            for st in self._io_streams:
+                for ev in prev["end"]:
+                    st.wait_event(ev)
+        run_events, out_events = [], []
+
+        def queue_in(lo, hi):
+            if same_plan:                                   # dry_d[lo:hi] is free once the previous step's kernels read it
+                s_in.wait_event(prev["run"][edges.index((lo, hi))])
+            with torch.cuda.stream(s_in):
                 if dry_fc_h is None:
                     dry_d[lo:hi].copy_(dry_h[lo:hi], non_blocking=True)
                 else:
@@ -189,18 +224,14 @@ class InterwovenRenderer:
                         pl = ph_long_h[r0:r1].to(dev, non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(s_in)
-                staged.append((ev_in, pl, po, r0, r1))
-        keep += [*f_all.values(), *p_all.values(), pst_all, offs_all]
+            keep.extend((pl, po))
+            return ev_in, pl, po, r0, r1
 
-        # ---- 2. per chunk: kernels, then the output copies
-        with torch.cuda.stream(s_run):
-            finish = None
-            if callable(mod_lo_h):
-                m_all = mod_lo_h()                          # device-side LFO synthesis, behind the first input copies
-                if isinstance(m_all, tuple):
-                    m_all, finish = m_all
-        for (lo, hi), (ev_in, pl, po, r0, r1) in zip(edges, staged):
+        # ---- kernels of one chunk on the compute stream, then its output copies on the copy-out stream
+        def run(lo, hi, ev_in, pl, po, r0, r1):
             s_run.wait_event(ev_in)
+            if same_plan:                                   # wet_d / logmel[lo:hi] are free once their last copies left
+                s_run.wait_event(prev["out"][edges.index((lo, hi))])
             with torch.cuda.stream(s_run):
                 f = {k: v[lo:hi] for k, v in f_all.items()}
                 p = {k: v[lo:hi] for k, v in p_all.items()}
@@ -213,7 +244,6 @@ class InterwovenRenderer:
                     dph = dry_d[lo:hi].view(hi - lo, N).index_select(0, self._groups(effect, lo, hi)[2].to(torch.int64))
                 ev_run = torch.cuda.Event()
                 ev_run.record(s_run)
-            keep += [pl, po]
             s_out.wait_event(ev_run)
             with torch.cuda.stream(s_out):
                 wet_h[lo:hi].copy_(wet_d[lo:hi], non_blocking=True)
@@ -225,17 +255,45 @@ class InterwovenRenderer:
                 if dph is not None:
                     dry_ph_h[r0:r1].copy_(dph, non_blocking=True)
                     keep.append(dph)
+                ev_out = torch.cuda.Event()
+                ev_out.record(s_out)
+            run_events.append(ev_run)
+            out_events.append(ev_out)
+
+        # ---- schedule: two chunks of input copies go out first (they keep the H2D engine busy for the next few
+        # milliseconds), then the LFO synthesis and the first chunk's kernels -- so the first output copy starts as early
+        # as it can -- then every remaining input copy in one go, then the remaining chunks
+        ahead = min(2, len(edges))
+        staged = [queue_in(*e) for e in edges[:ahead]]
+        finish = None
+        if callable(mod_lo_h):
+            with torch.cuda.stream(s_run):
+                m_all = mod_lo_h()                          # device-side LFO synthesis, behind the first input copies
+                if isinstance(m_all, tuple):
+                    m_all, finish = m_all
+        run(*edges[0], *staged[0])
+        staged += [queue_in(*e) for e in edges[ahead:]]
+        for e, st in zip(edges[1:], staged[1:]):
+            run(*e, *st)
+        end = []
         for st in self._io_streams:
             ev = torch.cuda.Event()
             ev.record(st)
-            cur.wait_event(ev)
-        ok = finish() if finish is not None else True       # read-back of the LFO synthesis, behind everything queued
-        cur.synchronize()                                   # everything has landed: `keep` may go
-        del keep
-        if not ok:
+            end.append(ev)
+        # read-back of the LFO synthesis (advances the host generator): its kernels ran long before the host got here
+        ok = finish() if finish is not None else True
+        self._prev_host_step = {"edges": edges, "run": run_events, "out": out_events, "end": end}
+        handle = _HostStep(end, keep, cur)
+        if not ok:                                          # device replay not usable (practically never): redo, blocking
+            handle.wait()
+            self._prev_host_step = None
             m = mod_lo_h(blocking=True)
-            self.render_host(dry_h, effect, m, fc_h, ph_h, wet_h, logmel, stat_h, chunk, dry_d, wet_d, logmel_h, ph_long_h,
-                             ph_start_h, dry_ph_h, dry_fc_h, ph_packed_h, ph_offsets)
+            return self.render_host(dry_h, effect, m, fc_h, ph_h, wet_h, logmel, stat_h, chunk, dry_d, wet_d, logmel_h,
+                                    ph_long_h, ph_start_h, dry_ph_h, dry_fc_h, ph_packed_h, ph_offsets, wait)
+        if wait:
+            handle.wait()
+            return None
+        return handle
 
     @torch.no_grad()
     def render(self, dry: Tensor, effect: Tensor, mod_lo: Tensor, fc: Dict[str, Tensor], ph: Dict[str, Tensor],

@@ -27,6 +27,20 @@ for _ in range(5):
     t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
 print("wall per step (no profiler): median %.1f ms, min %.1f ms" % (np.median(ts) * 1e3, min(ts) * 1e3))
 
+
+def burst(n):
+    h = None
+    for i in range(n):
+        nxt = step(wait=False, alt=i & 1)
+        if h is not None:
+            h.wait()
+        h = nxt
+    h.wait()
+
+
+burst(2)
+t0 = time.perf_counter(); burst(10); print("pipelined steps (render_host(wait=False)): %.1f ms per step" % ((time.perf_counter() - t0) * 100))
+
 ts = []
 for _ in range(5):
     t0 = time.perf_counter(); torch.manual_seed(43)
@@ -70,3 +84,12 @@ print("first device op starts %.2f ms after the first host op; host ops span %.1
 big = sorted(((e.time_range.end - e.time_range.start, e.name) for e in ev if "Memcpy" in e.name), reverse=True)[:3]
 for d, n in big:
     print("  longest copy: %.2f ms %s" % (d / 1e3, n))
+
+if os.environ.get("E2E_CPROFILE"):
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(5):
+        step()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(45)

@@ -204,3 +204,37 @@ def test_render_host_packed_phaser_rows_and_lfo_callable():
         assert torch.equal(wet_h, w_ref.cpu()) and torch.equal(lm, lm_ref)
         if want_dry:
             assert torch.equal(dry_ph_h, d_ref.cpu()[phx, 0])
+
+
+def test_render_host_pipelined_steps_equal_blocking_steps():
+    """render_host(wait=False): three consecutive steps with different inputs share the device buffers and overlap; each
+    lands exactly what its own blocking call produces (per-chunk events order the reuse of dry_d / wet_d / logmel)."""
+    from mod_extraction_b200.render import InterwovenRenderer
+    dev = torch.device("cuda", 0)
+    B = 23
+    R = InterwovenRenderer(bench.N, float(bench.SR), dev)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    steps = []
+    for seed in (21, 22, 23):
+        dry, effect, mod_lo, fc, ph = bench.oracle_inputs(B, seed=seed)
+        steps.append((pin(dry), torch.from_numpy(effect), pin(mod_lo), {k: pin(v) for k, v in fc.items()},
+                      {k: pin(v) for k, v in ph.items()}))
+    dry_d = torch.empty((B, 1, bench.N), device=dev)
+    wet_d, lm = R.alloc_outputs(B)
+    ref = []
+    for d, e, m, f, p in steps:
+        w = torch.empty((B, 1, bench.N)).pin_memory()
+        st = torch.empty((B, 2)).pin_memory()
+        R.render_host(d, e, m, f, p, w, lm, st, chunk=6, dry_d=dry_d, wet_d=wet_d)
+        ref.append((w.clone(), st.clone()))
+    outs, handles = [], []
+    for d, e, m, f, p in steps:
+        w = torch.empty((B, 1, bench.N)).pin_memory()
+        st = torch.empty((B, 2)).pin_memory()
+        handles.append(R.render_host(d, e, m, f, p, w, lm, st, chunk=6, dry_d=dry_d, wet_d=wet_d, wait=False))
+        outs.append((w, st))
+    for h in handles:
+        h.wait()
+        h.wait()                                                          # idempotent
+    for (w, st), (rw, rst) in zip(outs, ref):
+        assert torch.equal(w, rw) and torch.equal(st, rst)
