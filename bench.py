@@ -542,8 +542,10 @@ def run_config4(cx, args):
     units = {"logmel": ("bytes_per_row", B), "flanger": ("bytes_per_example", i_fl.numel()),
              "chorus": ("bytes_per_example", i_ch.numel()), "phaser": ("bytes_per_example", i_ph.numel())}
     for name, (key, n_units) in units.items():
+        ratio = traffic_tab.get(name, {}).get("per_algorithmic_byte")      # ncu DRAM bytes per algorithmic byte of the capture
         t = traffic_tab.get(name, {}).get(key)
-        kernels[name]["dram_traffic_bytes"] = None if t is None else t * n_units
+        kernels[name]["dram_traffic_bytes"] = (ratio * kernels[name]["algorithmic_bytes"] if ratio is not None else
+                                               (None if t is None else t * n_units))
     dom = max(kernels, key=lambda k: kernels[k]["ms"] * (2 if k == "logmel" else 1))
     gbs_pipe = step_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = roofline_block(kernels, dom, KERNEL_NAMES, peak, peak_src,
