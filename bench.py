@@ -664,8 +664,10 @@ def run_config4(cx, args):
                    "l2": "inputs (1.4 GB dry + 1.4 GB wet + 2.9 GB log-mel per step) far exceed the 126 MB L2",
                    "parallelism": f"batch-sharded x{world}, no collective while rendering"},
         "clocks": clocks, "e2e": e2e, "e2e_full": e2e_full, "with_lfo": with_lfo, "strong": strong,
-        "gpu_launches": args.steps * (1 + 2 + PHASER_LAUNCHES + 4),  # per step: flanger 1 + chorus 2 (CTA-per-example kernel, then
-        # the kernel for the rest, which finds nothing left) + phaser + log-mel 4
+        # per step (ncu launch list, profiles/r02_launches_all.txt): flanger 1 (fc_cta_kernel) + chorus 2 (fc_wide_kernel, then
+        # fc_cta_kernel for the rest, which finds nothing left) + phaser 2 (phaser_phase_kernel, phaser_fused_kernel; the
+        # memset of the look-back flags is the driver's) + log-mel 6 (wet rows of the three groups, dry rows of the three groups)
+        "gpu_launches": args.steps * (1 + 2 + 2 + 6),
         "roofline": roofline, "lfo_generation_s": lfo_gen_s, "metrics_gather_ms": gather_ms,
         "wet_abs_mean": checksum,
     }

@@ -195,6 +195,24 @@ def make_quasi_periodic(mod_sig: T,
 
 
 _PINNED_PAIRS: list = []        # recycled pinned (2,) int32 buffers of the deferred read-back
+_PINNED_STAGES: list = []       # (pinned float32 staging buffer, event after its last copy to the device)
+
+
+def _event_now():
+    ev = tr.cuda.Event()
+    ev.record()
+    return ev
+
+
+def _pinned_stage(n: int) -> T:
+    """A pinned float32 buffer of n elements whose previous host-to-device copy has completed."""
+    for i, (buf, ev) in enumerate(_PINNED_STAGES):
+        if buf.numel() == n and ev.query():
+            del _PINNED_STAGES[i]
+            return buf
+    if len(_PINNED_STAGES) > 8:
+        del _PINNED_STAGES[0]
+    return tr.empty((n,), dtype=tr.float32).pin_memory()
 
 
 def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes: List[str], device=None,
@@ -225,10 +243,18 @@ def make_combined_mod_sig_batch(n_samples: int, sr: float, freqs, phases, shapes
         assert not host_replay and not return_base and B > 0 and 3 <= n_samples <= 32767
         from ._rng import TorchMT
         mt = TorchMT()
-        words = tr.from_numpy(mt.words(B * 17).view("int32"))
-        out, _, consumed = _ops.combined_lfo(n_samples, sr, f.float().to(device, non_blocking=True),
-                                             p.float().to(device, non_blocking=True), sid.to(device),
-                                             words.to(device, non_blocking=True))
+        # every host operand goes through ONE pinned buffer and one asynchronous copy: a copy from pageable memory
+        # would make the host wait for whatever the stream is still running (the previous step's render)
+        n_words = B * 17
+        stage = _pinned_stage(2 * B + S + n_words)
+        stage[:B].copy_(f.float())
+        stage[B:2 * B].copy_(p.float())
+        stage[2 * B:2 * B + S].view(tr.int32).copy_(sid)
+        stage[2 * B + S:].view(tr.int32).copy_(tr.from_numpy(mt.words(n_words).view("int32")))
+        on_dev = stage.to(device, non_blocking=True)
+        _PINNED_STAGES.append((stage, _event_now()))
+        out, _, consumed = _ops.combined_lfo(n_samples, sr, on_dev[:B], on_dev[B:2 * B], on_dev[2 * B:2 * B + S].view(tr.int32),
+                                             on_dev[2 * B + S:].view(tr.int32))
 
         # the read-back is queued right behind the replay (pinned destination + event), so finish() waits for the LFO
         # kernels only, not for whatever the caller queues after them

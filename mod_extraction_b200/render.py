@@ -154,6 +154,8 @@ class InterwovenRenderer:
         must not be read before ``handle.wait()`` and should alternate between two sets when steps overlap."""
         B, _, N = dry_h.shape
         dev = self.device
+        if B == 0:
+            return None if wait else _HostStep([], [], torch.cuda.current_stream(dev))
         if dry_d is None:
             dry_d = torch.empty((B, 1, N), device=dev, dtype=torch.float32)
         if wet_d is None:
