@@ -475,7 +475,18 @@ struct FusedArgs {
     float2* ph;                 // (n_items, n_chunks): phase at the chunk's first control point, phase of the one before
 };
 
-// chunk-start phases: one thread per (example, host block), juce::dsp::Oscillator semantics (see phaser_ctl_kernel)
+// chunk-start phases: one thread per (example, host block), juce::dsp::Oscillator semantics (see phaser_ctl_kernel).
+// The float32 phase is a chain of sequential additions with the wrap at 2 pi, so a host block of 8192 samples is 2048
+// dependent steps whatever is done -- what can be kept short is the step: when the increment is below 2 pi (always, for
+// an LFO) the wrap is ONE conditional subtraction (p + inc < 4 pi), computed branch-free (add, subtract, select: 12 cycles
+// instead of a data-dependent loop), and every block is walked exactly once: the phase of a block's last control point,
+// which the next block's first chunk needs as its "control point before", is written there by the thread that walks it.
+__device__ __forceinline__ float phase_advance(float p, float inc, float two_pi) {
+    const float next = p + inc;
+    const float wrapped = next - two_pi;
+    return (next >= two_pi) ? wrapped : next;
+}
+
 __global__ void __launch_bounds__(128) phaser_phase_kernel(const FusedArgs f, int n_blocks) {
     const PhaserArgs& a = f.a;
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
@@ -483,6 +494,7 @@ __global__ void __launch_bounds__(128) phaser_phase_kernel(const FusedArgs f, in
     const int item = pair / n_blocks, blk = pair - item * n_blocks;
     const int b = example_of(a, item);
     const int need = f.start ? min(a.N, f.start[b] + f.n_out) : a.N;
+    // (a block past the window still has to hand its last phase to nobody: nothing after `need` is rendered)
     if ((int64_t)blk * a.block >= need) return;
     const float two_pi = MODFX_TWO_PI_F;
     const float sr_down = (float)((double)a.sr / (double)kUpd);
@@ -496,33 +508,29 @@ __global__ void __launch_bounds__(128) phaser_phase_kernel(const FusedArgs f, in
     const int s0 = blk * a.block, s1 = min(s0 + a.block, a.N);
     const int c0 = s0 / kChunk, c1 = (s1 + kChunk - 1) / kChunk;
     float2* out = f.ph + (int64_t)item * a.n_chunks;
-    // the control point before this block's first one is the previous block's last: redo that block's walk (the same
-    // sequence of float32 additions its own thread performs, so the value is bit-identical); a clip's very first
-    // control point has no predecessor and the value is unused (all filter states are zero there)
+    // a clip's very first control point has no predecessor and the value is unused (all filter states are zero there)
     float prev = 0.0f;
-    if (blk > 0) {
-        float q = 0.0f;
-        for (int i = 0; i < blk - 1; ++i) {
-            float next = q + inc * (float)(a.block / kUpd);
-            while (next >= two_pi) next -= two_pi;
-            q = next;
-        }
-        for (int j = 0; j < a.block / kUpd - 1; ++j) {
-            float next = q + inc;
-            while (next >= two_pi) next -= two_pi;
-            q = next;
-        }
-        prev = q;
-    }
+    const bool small = inc < two_pi;
     for (int c = c0; c < c1; ++c) {
-        out[c] = make_float2(p, prev);
-        for (int j = 0; j < kCtl; ++j) {
-            prev = p;
-            float next = p + inc;
-            while (next >= two_pi) next -= two_pi;
-            p = next;
+        out[c].x = p;
+        if (c > c0 || blk == 0) out[c].y = prev;     // the first chunk of a later block: written by the previous block's thread
+        if (small) {
+#pragma unroll 8
+            for (int j = 0; j < kCtl; ++j) {
+                prev = p;
+                p = phase_advance(p, inc, two_pi);
+            }
+        } else {
+            for (int j = 0; j < kCtl; ++j) {
+                prev = p;
+                float next = p + inc;
+                while (next >= two_pi) next -= two_pi;
+                p = next;
+            }
         }
     }
+    // this block's last control point is the one before the next block's first (only a full block has a successor)
+    if (s1 - s0 == a.block && c1 < a.n_chunks) out[c1].y = prev;
 }
 
 __device__ __forceinline__ float phaser_coef(float phase, float vol, float ctr, float log_span, float log_min, float w0) {
@@ -580,12 +588,19 @@ __global__ void __launch_bounds__(kFusedThreads) phaser_fused_kernel(const Fused
         float2 pp = (chunk < a.n_chunks) ? f.ph[(int64_t)item * a.n_chunks + chunk] : make_float2(0.0f, 0.0f);
         if (tid == 0) phs[0] = pp.y;                                      // control point before the segment
         float p = pp.x;
-#pragma unroll 4
-        for (int q = 0; q < kCtl; ++q) {
-            phs[1 + tid * kCtl + q] = p;
-            float next = p + inc;
-            while (next >= two_pi) next -= two_pi;
-            p = next;
+        if (inc < two_pi) {
+#pragma unroll 8
+            for (int q = 0; q < kCtl; ++q) {
+                phs[1 + tid * kCtl + q] = p;
+                p = phase_advance(p, inc, two_pi);
+            }
+        } else {
+            for (int q = 0; q < kCtl; ++q) {
+                phs[1 + tid * kCtl + q] = p;
+                float next = p + inc;
+                while (next >= two_pi) next -= two_pi;
+                p = next;
+            }
         }
     }
     __syncthreads();
