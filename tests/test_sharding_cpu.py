@@ -41,3 +41,16 @@ def test_all_gather_world2_gloo(n):
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
+
+
+def test_host_step_chunk_schedule_covers_the_batch():
+    """render_host's chunk schedule: contiguous, complete, a short first and last chunk for batches of several chunks."""
+    from mod_extraction_b200.render import InterwovenRenderer
+    for B, chunk in [(1, 512), (26, 7), (23, 6), (512, 512), (1100, 512), (4096, 512), (4096, 256), (4097, 384), (5, 1)]:
+        edges = InterwovenRenderer._chunk_edges(B, chunk)
+        assert edges[0][0] == 0 and edges[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        assert all(0 < hi - lo <= chunk + max(1, chunk // 4) for lo, hi in edges)
+        if B > 2 * chunk:
+            short = max(1, chunk // 4)
+            assert edges[0][1] - edges[0][0] == short and edges[-1][1] - edges[-1][0] <= short
