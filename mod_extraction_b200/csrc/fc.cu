@@ -24,6 +24,9 @@ constexpr int kTile = 128;          // samples per tile (4 sub-steps x 32 lanes)
 constexpr int kSub = kTile / kWarp; // 4
 constexpr int kLoWin = 512;         // control-rate LFO points staged in shared memory at a time
 constexpr int kStages = 8;          // dry-audio tiles in flight per warp (cp.async ring)
+#ifndef MODFX_FC_POLL_NS
+#define MODFX_FC_POLL_NS 128   // producers polling for the consumer: 32 / 100 / 300 ns measured within noise of each other (1.17-1.26 ms), longer leaves more issue slots
+#endif
 constexpr int kSerialMaxK = 7;      // register-history serial run covers tap distances up to this (+1)
 
 struct FcArgs {
@@ -762,7 +765,7 @@ __global__ void __launch_bounds__(kCtaThreads) fc_cta_kernel(const FcArgs a, int
                 const int td = t - kNT;
                 while (done_seen <= td) {
                     done_seen = ld_acquire(done);
-                    if (done_seen <= td) __nanosleep(32);   // leave the issue slots to the warps that have work
+                    if (done_seen <= td) __nanosleep(MODFX_FC_POLL_NS);   // leave the issue slots to the warps that have work
                 }
                 PR_STAT(0);
 #pragma unroll
