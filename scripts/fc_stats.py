@@ -61,3 +61,32 @@ if hasattr(L, "modfx_fc_serial_stats"):
     L.modfx_fc_serial_stats(buf)
     if buf[0]:
         print("serial_run: %d calls, %.1f blocks per call, %.0f cycles per call, %.1f cycles per sample inside the loop" % (buf[0], buf[1] / 8.0 / buf[0], buf[2] / buf[0], buf[3] / (4.0 * buf[1])))
+
+# ---- how well fc_cost_kernel's score predicts the measured consumer cycles, and what list scheduling makes of it
+A = (441.0 * p[2].cpu().numpy()).astype(np.float32)                 # Mlfo * width
+D0 = (44.0 * p[1].cpu().numpy()).astype(np.float32)                 # min_delay_width * Mmin
+d = A[:, None] * lo.cpu().numpy() + D0[:, None]
+cost = np.where(d < 1.0, 1.0, np.where(d < 9.0, 16.0, np.where(d < 33.0, 1.0 + 60.0 / np.maximum(d - 1.0, 1e-3), np.where(d < 129.0, 1.5, 1.0))))
+score = cost.sum(1)
+rk = lambda v: np.argsort(np.argsort(v))
+print("rank correlation of the predicted cost with the measured consumer cycles: %.3f" % np.corrcoef(rk(score), rk(tot))[0, 1])
+lin = np.polyfit(score, tot, 1)
+print("measured cycles ~ %.1f * score + %.0f; residual rms %.0f cycles (mean %.0f)" % (lin[0], lin[1], np.sqrt(np.mean((np.polyval(lin, score) - tot) ** 2)), tot.mean()))
+
+
+def makespan(order_, slots=148 * 7):
+    import heapq
+    free = [0.0] * slots
+    heapq.heapify(free)
+    end = 0.0
+    for i in order_:
+        t = heapq.heappop(free) + tot[i]
+        end = max(end, t)
+        heapq.heappush(free, t)
+    return end / 1.965e6
+
+
+if B > 148 * 7:
+    print("list scheduling on %d slots with the measured per-example cycles: index order %.3f ms, by predicted cost %.3f ms, "
+          "by measured cost %.3f ms; sum / slots %.3f ms" % (148 * 7, makespan(range(B)), makespan(np.argsort(-score)),
+                                                               makespan(np.argsort(-tot)), tot.sum() / (148 * 7) / 1.965e6))
