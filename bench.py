@@ -460,11 +460,11 @@ def make_e2e_step(cx, R, wb, chunk):
         torch.manual_seed(43 + rank)
         return make_combined_mod_sig_batch(n_lo, SR // 100, wb["rate"], wb["phase"], SHAPES6, device=dev, deferred=not blocking)
 
-    def e2e_step(logmel_h=None, wait=True, alt=0):
+    def e2e_step(logmel_h=None, wait=True, alt=0, duplex=True):
         # host (rate, phase) + generator state in, pinned dry audio in; wet audio (+ log-mel) out to pinned host
         return R.render_host(dry_h, wb["effect"], lfos, fc_h, ph_h, wet_hs[alt], logmel, stat_hs[alt], chunk=chunk,
                              dry_d=dry_d, wet_d=wet, logmel_h=logmel_h, ph_packed_h=ph_packed_h, ph_offsets=offs,
-                             ph_start_h=ph_start_h, dry_fc_h=dry_fc_h, wait=wait)
+                             ph_start_h=ph_start_h, dry_fc_h=dry_fc_h, wait=wait, duplex=duplex)
     return e2e_step, {"h2d": h2d, "d2h": d2h}
 
 
@@ -589,9 +589,20 @@ def run_config4(cx, args):
 
         n_e2e = max(3, min(args.steps, 10))
         dt_serial = host_timed(e2e_step, n_e2e)
-        dt = host_timed_pipelined(n_e2e)
+        dt_pipe = host_timed_pipelined(n_e2e)
+        dt_half = host_timed(lambda: e2e_step(duplex=False), n_e2e) if world > 1 else float("inf")
+        # Three schedules of the same public call.  Steps pipelined (wait=False) keep both copy directions busy all the
+        # time: fastest on a host that sustains full duplex (one rank: 34 vs 38 ms), slower where several ranks share a
+        # host whose duplex rate collapses (two ranks on these boxes: 65 vs 52 ms); there, holding the output copies back
+        # until the inputs are in (duplex=False) can win.  The headline is the fastest schedule; all are shown.
+        dt, schedule = min((dt_pipe, "steps pipelined (render_host(wait=False))"),
+                           (dt_serial, "one step at a time (render_host(wait=True))"),
+                           (dt_half, "one step at a time, one copy direction at a time (render_host(duplex=False))"))
         e2e = {"value": world * B * (N / SR) / dt, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": n_e2e, "chunk": args.e2e_chunk,
+               "schedule": schedule,
+               "steps_pipelined": {"ms": dt_pipe * 1e3, "value": world * B * (N / SR) / dt_pipe},
+               "half_duplex": None if world == 1 else {"ms": dt_half * 1e3, "value": world * B * (N / SR) / dt_half},
                "one_step_alone": {"ms": dt_serial * 1e3, "value": world * B * (N / SR) / dt_serial,
                                   "note": "the same call with every step synchronised before the next one starts (latency of "
                                           "one step: first input byte to last output byte)"},
@@ -600,9 +611,10 @@ def run_config4(cx, args):
                        "that determine its window) + parameters in, LFO synthesis on the device from host (rate, phase) + "
                        "generator words behind the first copies, wet audio + per-example log-mel mean out (the dry windows of "
                        "the phaser examples are slices of host data and are not copied back), chunks pipelined over "
-                       "copy/compute/copy streams and consecutive steps pipelined the same way (render_host(wait=False): step "
-                       "i+1 is queued while the last output copies of step i drain, two alternating sets of pinned output "
-                       "buffers; timed from the first call to the last byte of the last step); the (B,2,256,345) log-mel "
+                       "copy/compute/copy streams; measured one step at a time and with consecutive steps pipelined the same way "
+                       "(render_host(wait=False): step i+1 is queued while the last output copies of step i drain, two "
+                       "alternating sets of pinned output buffers; timed from the first call to the last byte of the last "
+                       "step), the faster schedule is the headline (`schedule`); the (B,2,256,345) log-mel "
                        "tensor stays in HBM where the extractor consumes it (e2e_full delivers it to the host too)"}
         if not args.no_e2e_full:
             try:

@@ -118,7 +118,7 @@ class InterwovenRenderer:
                     logmel_h: Optional[Tensor] = None, ph_long_h: Optional[Tensor] = None,
                     ph_start_h: Optional[Tensor] = None, dry_ph_h: Optional[Tensor] = None,
                     dry_fc_h: Optional[Tensor] = None, ph_packed_h: Optional[Tensor] = None,
-                    ph_offsets=None, wait: bool = True):
+                    ph_offsets=None, wait: bool = True, duplex: bool = True):
         """Host-buffer entry point: pinned host dry audio + parameters in, wet audio out to the pinned host
         tensor `wet_h`; the log-mel tensor stays on the GPU (`logmel`, (B,2,n_mels,n_frames)) where the
         extractor consumes it, and `stat_h` (B, 2) receives its per-example mean; with `logmel_h` (pinned, same
@@ -151,7 +151,12 @@ class InterwovenRenderer:
         have landed): the next call may be issued before that, and its input copies then run while this step's last
         output copies drain -- consecutive steps are pipelined like chunks are.  The device buffers ``dry_d`` / ``wet_d``
         / ``logmel`` may be the same in consecutive calls (per-chunk events order the reuse); the HOST output buffers
-        must not be read before ``handle.wait()`` and should alternate between two sets when steps overlap."""
+        must not be read before ``handle.wait()`` and should alternate between two sets when steps overlap.
+
+        ``duplex=False`` holds every output copy back until the last input copy of the step has finished: the link then
+        carries one direction at a time.  Slower on a host that sustains full duplex (one rank: both directions overlap
+        almost completely), faster where several ranks share a host whose copy rate collapses when both directions run
+        (measured with eight ranks: 233 GB/s in alone, 120 GB/s out alone, 77 GB/s per direction together)."""
         B, _, N = dry_h.shape
         dev = self.device
         if B == 0:
@@ -247,6 +252,8 @@ class InterwovenRenderer:
                 ev_run = torch.cuda.Event()
                 ev_run.record(s_run)
             s_out.wait_event(ev_run)
+            if not duplex:
+                s_out.wait_event(staged[-1][0])             # the last input copy of the step
             with torch.cuda.stream(s_out):
                 wet_h[lo:hi].copy_(wet_d[lo:hi], non_blocking=True)
                 if logmel_h is not None:
@@ -265,7 +272,7 @@ class InterwovenRenderer:
         # ---- schedule: two chunks of input copies go out first (they keep the H2D engine busy for the next few
         # milliseconds), then the LFO synthesis and the first chunk's kernels -- so the first output copy starts as early
         # as it can -- then every remaining input copy in one go, then the remaining chunks
-        ahead = min(2, len(edges))
+        ahead = min(2, len(edges)) if duplex else len(edges)
         staged = [queue_in(*e) for e in edges[:ahead]]
         finish = None
         if callable(mod_lo_h):
@@ -291,7 +298,7 @@ class InterwovenRenderer:
             self._prev_host_step = None
             m = mod_lo_h(blocking=True)
             return self.render_host(dry_h, effect, m, fc_h, ph_h, wet_h, logmel, stat_h, chunk, dry_d, wet_d, logmel_h,
-                                    ph_long_h, ph_start_h, dry_ph_h, dry_fc_h, ph_packed_h, ph_offsets, wait)
+                                    ph_long_h, ph_start_h, dry_ph_h, dry_fc_h, ph_packed_h, ph_offsets, wait, duplex)
         if wait:
             handle.wait()
             return None

@@ -199,7 +199,8 @@ def test_render_host_packed_phaser_rows_and_lfo_callable():
             return to(mod_lo)
         R.render_host(torch.empty((B, 1, bench.N), device="meta"), eff, lfos, {k: pin(v) for k, v in fc.items()},
                       {k: pin(v) for k, v in ph.items()}, wet_h, lm, None, chunk=5, ph_packed_h=pin(packed), ph_offsets=offs,
-                      ph_start_h=pin(start), dry_ph_h=dry_ph_h, dry_fc_h=pin(dry[fcx, 0]))
+                      ph_start_h=pin(start), dry_ph_h=dry_ph_h, dry_fc_h=pin(dry[fcx, 0]),
+                      duplex=not want_dry)                                # both copy schedules give the same bytes
         assert len(calls) == 1
         assert torch.equal(wet_h, w_ref.cpu()) and torch.equal(lm, lm_ref)
         if want_dry:
