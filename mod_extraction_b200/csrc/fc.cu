@@ -955,6 +955,26 @@ __global__ void __launch_bounds__(kCtaThreads) fc_cta_kernel(const FcArgs a, int
                     wr[j * kWarp] = __fadd_rn(r[j].x, __fmul_rn(c.fb, it));                             // fx.py:114
                     itb[j * kWarp + lane] = it;
                 }
+            } else if (sk[1] > kWarp && sk[3] > kWarp) {
+                // ---- every tap lies more than 64 samples back within a pair of blocks (delays of 64 .. 128 samples): two
+                // waves of 64 samples, half the dependent steps of the four-wave path below ----
+#pragma unroll
+                for (int h = 0; h < kSub; h += 2) {
+                    float vp[2], vq[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const unsigned pk = __float_as_uint(r[h + j].w);
+                        vp[j] = smem[pk >> 16];
+                        vq[j] = smem[pk & 0xffffu];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float it = __fadd_rn(__fmul_rn(r[h + j].y, vq[j]), __fmul_rn(r[h + j].z, vp[j]));    // fx.py:113
+                        wr[(h + j) * kWarp] = __fadd_rn(r[h + j].x, __fmul_rn(c.fb, it));                           // fx.py:114
+                        itb[(h + j) * kWarp + lane] = it;
+                    }
+                    __syncwarp();
+                }
             } else {
                 // ---- no tap of a block falls inside that block: four waves, nothing but the taps in between ----
 #pragma unroll

@@ -113,13 +113,15 @@ def test_flanger_worst_case_serial_delays():
 
 
 def test_flanger_every_schedule_of_the_kernel():
-    """Constant delays of 0.5 .. 9.5, 31.5, 32.5, 127.5, 128.5 samples and slow ramps across those
+    """Constant delays of 0.5 .. 9.5, 31.5, 32.5, 64 .. 128.5 samples and slow ramps across those
     boundaries: exercises the register-history serial run for every tap distance K, the wave
-    schedule, the one-wave block and the 128-sample tile, plus the transitions between them."""
+    schedule, the one-wave block, the two-wave and the one-shot 128-sample tile, plus the transitions between
+    them."""
     from mod_extraction_b200.fx import MonoFlangerChorusModule
     N = 12000
-    delays = [0.0, 0.5, 1.0, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5, 8.5, 9.5, 15.25, 31.5, 32.5, 64.0, 127.5, 128.5, 300.0]
-    ramps = [(0.0, 12.0), (12.0, 0.0), (6.0, 40.0), (140.0, 20.0), (0.0, 484.0)]
+    delays = [0.0, 0.5, 1.0, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5, 8.5, 9.5, 15.25, 31.5, 32.5, 64.0, 65.5, 96.5, 127.5, 128.5,
+              300.0]
+    ramps = [(0.0, 12.0), (12.0, 0.0), (6.0, 40.0), (140.0, 20.0), (0.0, 484.0), (60.0, 135.0)]
     B = len(delays) + len(ramps)
     x = white((B, 1, N), 77)
     mod = np.zeros((B, N), dtype=np.float32)
