@@ -4,9 +4,14 @@
 // python loop costs ~105 us per time step.  Bit-exact with it: every float32 operation of the
 // reference is one IEEE-RN operation here (explicit __f*_rn intrinsics, never contracted).
 //
+// Three kernels share the per-sample arithmetic (=> the same bits): fc_cta_kernel (default: a CTA of three producer
+// warps + one consumer warp per delay line), fc_wide_kernel (a CTA per delay line whose every tap lies more than 384
+// samples back: the chorus) and fc_kernel (one warp per delay line: the first schedule, kept as the cross-check);
+// fc_allpass_kernel is the all-pass interpolation mode.
+//
 // Parallelisation (DESIGN.md "E1"): the recurrence v[n] = x[n] + fb*interp(v[n-kp], v[n-kq]) is
 // sequential in time per delay line, but a sample only depends on samples at least
-// `near = min(kp,kq)` steps back.  One warp owns one delay line (example x channel); the written
+// `near = min(kp,kq)` steps back.  In fc_kernel one warp owns one delay line (example x channel); the written
 // values v live in a shared-memory ring indexed by time.  A tile of 128 samples (4 per lane) is
 // rendered in one shot when every dependency falls before the tile (always true for chorus,
 // true for flanger while the delay exceeds 128 samples); otherwise 32-sample blocks are resolved
