@@ -626,43 +626,61 @@ __device__ __noinline__ void serial_run(float* __restrict__ ring, int mask, int 
 #ifdef MODFX_FC_STATS
     const long long sr_t0 = clock64();
 #endif
-    // w[3 + j] = v[g0 - j] for j >= 1 (history before the current group of 4 samples), w[3 - u] = sample u of the group:
-    // the tap of sample u at distance d is w[3 - u + d] whether it lies before the group or inside it.
-    float w[K + 5];
+    // Two groups of 4 samples per loop iteration, A then B, over ONE register window w[]: for a group with base `o`,
+    // w[o + 3 - u] is sample u of the group and w[o + 3 + j] the sample j before the group, so the tap of sample u at
+    // distance d is w[o + 3 - u + d] whether it lies before the group or inside it.  A works at o = 4, B at o = 0 (B's
+    // history starts with A's outputs, no copy), the window slides by 8 once per iteration and the coefficient records of
+    // the two groups live in two register sets that swap roles -- the moves that a one-group loop spends on shifting the
+    // window and on "current = next" every 4 samples sat right behind the dependent chain, where nothing hides them.
+    float w[K + 9];
 #pragma unroll
-    for (int j = 1; j <= K + 1; ++j) w[3 + j] = ring[(nb - j) & mask];
+    for (int j = 1; j <= K + 1; ++j) w[7 + j] = ring[(nb - j) & mask];
     float4* dst = reinterpret_cast<float4*>(ring + (nb & mask));    // tiles are 128-aligned, the ring a multiple of 128
     float4* ito = reinterpret_cast<float4*>(it_out);
-    float4 cur[4], nxt[4];
+    float4 ca[4], cb[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) cur[u] = coef[u];
+    for (int u = 0; u < 4; ++u) ca[u] = coef[u];
 #ifdef MODFX_FC_STATS
     const long long sr_t1 = clock64();
 #endif
+#define MODFX_SERIAL_GROUP(O, CF, ITS)                                                                              \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                                 \
+        const float4 cf = CF[u];                                                                                    \
+        const float far = (K == 1) ? cf.w : __fmul_rn(cf.w, w[(O) + 3 - u + K + 1]);                                \
+        const float it = __fadd_rn(__fmul_rn(cf.y, w[(O) + 3 - u + (K == 1 ? 1 : K - 1)]),                          \
+                                   __fadd_rn(__fmul_rn(cf.z, w[(O) + 3 - u + (K == 1 ? 2 : K)]), far)); /* fx.py:113 */ \
+        ITS[u] = it;                                                                                                \
+        w[(O) + 3 - u] = __fadd_rn(cf.x, __fmul_rn(fb, it));                                            /* fx.py:114 */ \
+    }
+    const int last = ngroups - 1;
 #pragma unroll 1
-    for (int g = 0; g < ngroups; ++g) {
-        const int gn = min(g + 1, ngroups - 1);
+    for (int g = 0; g < ngroups; g += 2) {
+        {
+            const int gn = min(g + 1, last);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) nxt[u] = coef[4 * gn + u];
-        float its[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float4 cf = cur[u];
-            const float far = (K == 1) ? cf.w : __fmul_rn(cf.w, w[3 - u + K + 1]);
-            const float it = __fadd_rn(__fmul_rn(cf.y, w[3 - u + (K == 1 ? 1 : K - 1)]),
-                                       __fadd_rn(__fmul_rn(cf.z, w[3 - u + (K == 1 ? 2 : K)]), far));     // fx.py:113
-            its[u] = it;
-            w[3 - u] = __fadd_rn(cf.x, __fmul_rn(fb, it));                                                 // fx.py:114
+            for (int u = 0; u < 4; ++u) cb[u] = coef[4 * gn + u];
         }
+        float its[4];
+        MODFX_SERIAL_GROUP(4, ca, its)
         if (lane == 0) {            // every lane holds the same values: one lane stores
-            dst[g] = make_float4(w[3], w[2], w[1], w[0]);
+            dst[g] = make_float4(w[7], w[6], w[5], w[4]);
             ito[g] = make_float4(its[0], its[1], its[2], its[3]);
         }
+        if (g + 1 >= ngroups) break;
+        {
+            const int gn = min(g + 2, last);
 #pragma unroll
-        for (int k = K + 4; k >= 4; --k) w[k] = w[k - 4];
+            for (int u = 0; u < 4; ++u) ca[u] = coef[4 * gn + u];
+        }
+        MODFX_SERIAL_GROUP(0, cb, its)
+        if (lane == 0) {
+            dst[g + 1] = make_float4(w[3], w[2], w[1], w[0]);
+            ito[g + 1] = make_float4(its[0], its[1], its[2], its[3]);
+        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+        for (int k = K + 8; k >= 8; --k) w[k] = w[k - 8];
     }
+#undef MODFX_SERIAL_GROUP
 #ifdef MODFX_FC_STATS
     if (lane == 0) {
         const long long sr_t2 = clock64();
