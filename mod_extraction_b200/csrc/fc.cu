@@ -626,15 +626,15 @@ __device__ __noinline__ void serial_run(float* __restrict__ ring, int mask, int 
 #ifdef MODFX_FC_STATS
     const long long sr_t0 = clock64();
 #endif
-    // Two groups of 4 samples per loop iteration, A then B, over ONE register window w[]: for a group with base `o`,
+    // Four groups of 4 samples per loop iteration over ONE register window w[]: for a group with base `o`,
     // w[o + 3 - u] is sample u of the group and w[o + 3 + j] the sample j before the group, so the tap of sample u at
-    // distance d is w[o + 3 - u + d] whether it lies before the group or inside it.  A works at o = 4, B at o = 0 (B's
-    // history starts with A's outputs, no copy), the window slides by 8 once per iteration and the coefficient records of
-    // the two groups live in two register sets that swap roles -- the moves that a one-group loop spends on shifting the
+    // distance d is w[o + 3 - u + d] whether it lies before the group or inside it.  The groups work at o = 12, 8, 4, 0
+    // (each one's history starts with its predecessor's outputs, no copy), the window slides by 16 once per iteration and
+    // the coefficient records of consecutive groups live in two register sets that swap roles -- the moves that a one-group loop spends on shifting the
     // window and on "current = next" every 4 samples sat right behind the dependent chain, where nothing hides them.
-    float w[K + 9];
+    float w[K + 17];
 #pragma unroll
-    for (int j = 1; j <= K + 1; ++j) w[7 + j] = ring[(nb - j) & mask];
+    for (int j = 1; j <= K + 1; ++j) w[15 + j] = ring[(nb - j) & mask];
     float4* dst = reinterpret_cast<float4*>(ring + (nb & mask));    // tiles are 128-aligned, the ring a multiple of 128
     float4* ito = reinterpret_cast<float4*>(it_out);
     float4 ca[4], cb[4];
@@ -652,34 +652,39 @@ __device__ __noinline__ void serial_run(float* __restrict__ ring, int mask, int 
         ITS[u] = it;                                                                                                \
         w[(O) + 3 - u] = __fadd_rn(cf.x, __fmul_rn(fb, it));                                            /* fx.py:114 */ \
     }
-    const int last = ngroups - 1;
-#pragma unroll 1
-    for (int g = 0; g < ngroups; g += 2) {
-        {
-            const int gn = min(g + 1, last);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) cb[u] = coef[4 * gn + u];
-        }
-        float its[4];
-        MODFX_SERIAL_GROUP(4, ca, its)
-        if (lane == 0) {            // every lane holds the same values: one lane stores
-            dst[g] = make_float4(w[7], w[6], w[5], w[4]);
-            ito[g] = make_float4(its[0], its[1], its[2], its[3]);
-        }
-        if (g + 1 >= ngroups) break;
-        {
-            const int gn = min(g + 2, last);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) ca[u] = coef[4 * gn + u];
-        }
-        MODFX_SERIAL_GROUP(0, cb, its)
-        if (lane == 0) {
-            dst[g + 1] = make_float4(w[3], w[2], w[1], w[0]);
-            ito[g + 1] = make_float4(its[0], its[1], its[2], its[3]);
-        }
-#pragma unroll
-        for (int k = K + 8; k >= 8; --k) w[k] = w[k - 8];
+    // one group: prefetch the records of group G + 1 into NEXT, resolve group G from CUR at window base O, store
+#define MODFX_SERIAL_STEP(G, O, CUR, NEXT)                                                                          \
+    {                                                                                                               \
+        const int gn = min((G) + 1, last);                                                                          \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) NEXT[u] = coef[4 * gn + u];                                   \
+        float its[4];                                                                                               \
+        MODFX_SERIAL_GROUP(O, CUR, its)                                                                             \
+        if (lane == 0) {            /* every lane holds the same values: one lane stores */                         \
+            dst[G] = make_float4(w[(O) + 3], w[(O) + 2], w[(O) + 1], w[(O)]);                                       \
+            ito[G] = make_float4(its[0], its[1], its[2], its[3]);                                                   \
+        }                                                                                                           \
     }
+    const int last = ngroups - 1;
+    int g = 0;
+#pragma unroll 1
+    for (; g + 4 <= ngroups; g += 4) {
+        MODFX_SERIAL_STEP(g, 12, ca, cb)
+        MODFX_SERIAL_STEP(g + 1, 8, cb, ca)
+        MODFX_SERIAL_STEP(g + 2, 4, ca, cb)
+        MODFX_SERIAL_STEP(g + 3, 0, cb, ca)
+#pragma unroll
+        for (int k = K + 16; k >= 16; --k) w[k] = w[k - 16];
+    }
+    // (the callers hand over whole 32-sample blocks, 8 groups each, so nothing is left; kept for other group counts)
+#pragma unroll 1
+    for (; g < ngroups; ++g) {
+        MODFX_SERIAL_STEP(g, 12, ca, cb)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ca[u] = cb[u];
+#pragma unroll
+        for (int k = K + 16; k >= 16; --k) w[k] = w[k - 4];
+    }
+#undef MODFX_SERIAL_STEP
 #undef MODFX_SERIAL_GROUP
 #ifdef MODFX_FC_STATS
     if (lane == 0) {
